@@ -112,9 +112,19 @@ def gen_ranking():
             brand = aspects.permute((1, 0, 2)).mean(0)          # evaluator.py:93-94
             scores = ref_eval.cal_sim(brand, torch.from_numpy(posts)).numpy().copy()
             res = ref_eval.test_post_ranking(nb, 'auc', mdl, torch.from_numpy(posts), torch.from_numpy(lab))
+            # evaluator.py:124 uses np.argsort(-d), whose order under ties is unspecified (not stable on
+            # this AVX-512 host).  Second run with the stated tie-break: argsort forced to kind='stable'.
+            orig_argsort = np.argsort
+            np.argsort = lambda a, *args, **kw: orig_argsort(a, kind='stable')
+            try:
+                res_stable = ref_eval.test_post_ranking(nb, 'auc', mdl, torch.from_numpy(posts),
+                                                        torch.from_numpy(lab))
+            finally:
+                np.argsort = orig_argsort
         none_res = ref_eval.test_post_ranking(nb, 'recall', mdl, torch.from_numpy(posts), torch.from_numpy(lab))
         assert none_res is None
         save("ranking_%s.npz" % name, result=np.array([float(x) for x in res], dtype=np.float64),
+             result_stable=np.array([float(x) for x in res_stable], dtype=np.float64),
              scores=scores, brand=brand.numpy())
 
 
