@@ -1,0 +1,70 @@
+"""ctypes binding of libfrx_b200.so (C ABI in include/frx.h).
+
+There is NO CPU fallback: if the shared library has not been built, importing any
+compute entry point raises, and every compute call fails loudly on a box without an
+sm_100 GPU (frx_device_check).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfrx_b200.so")
+
+c_i32, c_i64, c_f32, c_sz, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t, ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/frx.h one to one
+SIGNATURES = {
+    "frx_abi_version": (c_i32, []),
+    "frx_last_error": (ctypes.c_char_p, []),
+    "frx_device_check": (c_i32, [c_i32]),
+    "frx_finalize_posts": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
+    "frx_brand_embed": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "frx_score_topk_workspace_bytes": (c_sz, [c_i32, c_i64, c_i32, c_i32]),
+    "frx_score_topk": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp,
+                               c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "frx_score_dense": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp]),
+    "frx_score_count": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "frx_topk_merge": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
+    "frx_label_stats": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "frx_rank_from_topk": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "frx_group_positives": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "frx_auc_rows": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "frx_triplet_workspace_bytes": (c_sz, [c_i32, c_i32]),
+    "frx_triplet_fwd_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "frx_contrastive_workspace_bytes": (c_sz, [c_i32, c_i32, c_i32]),
+    "frx_contrastive_fwd_bwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_f32, c_f32, c_i32,
+                                        c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "frx_normalize_rows": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp]),
+}
+
+_lib = None
+
+
+class FrxError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libfrx_b200.so (once) and declare every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FrxError(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(fancyrec_b200 has no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.frx_abi_version() != 1:
+        raise FrxError("libfrx_b200.so ABI version %d, expected 1" % lib.frx_abi_version())
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().frx_last_error().decode("utf8", "replace")
+        raise FrxError("%s failed (code %d): %s" % (what, rc, msg))

@@ -1,0 +1,80 @@
+// Shared helpers for libfrx_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <math.h>
+
+#include "../../include/frx.h"
+
+namespace frx {
+
+void set_error(const char* fmt, ...);
+
+#define FRX_CHECK_ARG(cond, ...)                    \
+  do {                                              \
+    if (!(cond)) {                                  \
+      frx::set_error(__VA_ARGS__);                  \
+      return FRX_E_ARG;                             \
+    }                                               \
+  } while (0)
+
+#define FRX_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      frx::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return FRX_E_CUDA;                                                                 \
+    }                                                                                    \
+  } while (0)
+
+#define FRX_LAUNCH_CHECK()                                                               \
+  do {                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess) {                                                            \
+      frx::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return FRX_E_CUDA;                                                                 \
+    }                                                                                    \
+  } while (0)
+
+int num_sms();
+
+// ---------------------------------------------------------------------------------------------
+// Total order used everywhere: (score descending, post index ascending).
+// A candidate is packed into one u64 key so that "larger key" == "ranks earlier":
+//   high 32 bits: order-preserving transform of the fp32 score (-0.0 folded into +0.0 so that the
+//                 two zeros tie, as they do under Python's float comparison at evaluator.py:109)
+//   low  32 bits: ~index  (smaller index -> larger key)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t score_to_ordered(float s) {
+  s = s + 0.0f;
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(s);
+#else
+  union { float f; uint32_t u; } cv; cv.f = s; uint32_t u = cv.u;
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_score(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } cv; cv.u = u; return cv.f;
+#endif
+}
+__host__ __device__ __forceinline__ unsigned long long make_key(float s, uint32_t index) {
+  return ((unsigned long long)score_to_ordered(s) << 32) | (unsigned long long)(0xFFFFFFFFu - index);
+}
+__host__ __device__ __forceinline__ float key_score(unsigned long long k) { return ordered_to_score((uint32_t)(k >> 32)); }
+__host__ __device__ __forceinline__ uint32_t key_index(unsigned long long k) { return 0xFFFFFFFFu - (uint32_t)k; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace frx

@@ -1,0 +1,253 @@
+// A1-A4: post-embedding finalisation (frame mean-pool -> per-branch l2norm -> concat -> row l2norm
+// -> fp32 / bf16) as ONE pass over HBM, and the brand embedding (W.E)/A without the [NB,A,D]
+// intermediate.  HBM-bound streaming kernels: 128-bit loads, one CTA per post row, the pooled row is
+// staged in shared memory so every input byte is read exactly once and every output byte written once.
+//
+// Reference lines replaced: util/data_provider.py:40,91,132 (torch.mean(frames, 0)),
+// model.py:39-44 (l2norm), model.py:482-485 (cat), evaluator.py:14-19,27-28, model.py:419-428,594.
+#include "common.cuh"
+
+namespace frx {
+
+constexpr int kFinThreads = 256;
+
+struct FinalizeParams {
+  const float* visual;
+  const int64_t* row_ptr;
+  const int32_t* row_idx;
+  const float* text;
+  int64_t n_posts;
+  int dv, dt, flags;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  int64_t ld_bf16;
+};
+
+__device__ __forceinline__ float2 block_sum2(float a, float b, float* red /* [2*32] */) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();   // protect `red` from the previous use
+  if (lane == 0) { red[warp] = a; red[32 + warp] = b; }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  float x = lane < nw ? red[lane] : 0.f;
+  float y = lane < nw ? red[32 + lane] : 0.f;
+  x = warp_sum(x);
+  y = warp_sum(y);
+  return make_float2(x, y);
+}
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+  using T = float4;
+  static __device__ __forceinline__ T ld(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ void add(T& a, const T& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+  static __device__ __forceinline__ void div(T& a, float d) { a.x /= d; a.y /= d; a.z /= d; a.w /= d; }
+  static __device__ __forceinline__ float sq(const T& a) { return a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w; }
+  static __device__ __forceinline__ void st(float* p, const T& a) { *reinterpret_cast<float4*>(p) = a; }
+  static __device__ __forceinline__ T lds(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void st_bf16(__nv_bfloat16* p, const T& a) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+template <>
+struct Vec<1> {
+  using T = float;
+  static __device__ __forceinline__ T ld(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ T zero() { return 0.f; }
+  static __device__ __forceinline__ void add(T& a, const T& b) { a += b; }
+  static __device__ __forceinline__ void div(T& a, float d) { a /= d; }
+  static __device__ __forceinline__ float sq(const T& a) { return a * a; }
+  static __device__ __forceinline__ void st(float* p, const T& a) { *p = a; }
+  static __device__ __forceinline__ T lds(const float* p) { return *p; }
+  static __device__ __forceinline__ void st_bf16(__nv_bfloat16* p, const T& a) { *p = __float2bfloat16_rn(a); }
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams P) {
+  extern __shared__ __align__(16) float row[];   // [dv + dt]
+  __shared__ float red[64];
+  using V = Vec<VEC>;
+  const int d = P.dv + P.dt;
+  const int tid = threadIdx.x;
+
+  for (int64_t p = blockIdx.x; p < P.n_posts; p += gridDim.x) {
+    // ---- pass A: global -> smem (mean-pool the visual branch), per-branch sum of squares ----
+    float ssv = 0.f, sst = 0.f;
+    int64_t r0 = p, r1 = p + 1;
+    if (P.row_ptr) { r0 = P.row_ptr[p]; r1 = P.row_ptr[p + 1]; }
+    const float nf = (float)(r1 - r0);
+    for (int c = tid * VEC; c < P.dv; c += kFinThreads * VEC) {
+      typename V::T acc = V::zero();
+      int64_t r = r0;
+      // 4 independent 128-bit loads in flight per thread; summed in frame order
+      for (; r + 4 <= r1; r += 4) {
+        int64_t i0 = r, i1 = r + 1, i2 = r + 2, i3 = r + 3;
+        if (P.row_idx) { i0 = P.row_idx[i0]; i1 = P.row_idx[i1]; i2 = P.row_idx[i2]; i3 = P.row_idx[i3]; }
+        typename V::T a0 = V::ld(P.visual + i0 * P.dv + c), a1 = V::ld(P.visual + i1 * P.dv + c);
+        typename V::T a2 = V::ld(P.visual + i2 * P.dv + c), a3 = V::ld(P.visual + i3 * P.dv + c);
+        V::add(acc, a0); V::add(acc, a1); V::add(acc, a2); V::add(acc, a3);
+      }
+      for (; r < r1; ++r) {
+        int64_t i0 = P.row_idx ? (int64_t)P.row_idx[r] : r;
+        typename V::T a0 = V::ld(P.visual + i0 * P.dv + c);
+        V::add(acc, a0);
+      }
+      if (P.row_ptr) V::div(acc, nf);          // torch.mean on CPU = sum / F (0 frames -> NaN)
+      ssv += V::sq(acc);
+      V::st(row + c, acc);
+    }
+    for (int c = tid * VEC; c < P.dt; c += kFinThreads * VEC) {
+      typename V::T a = V::ld(P.text + p * P.dt + c);
+      sst += V::sq(a);
+      V::st(row + P.dv + c, a);
+    }
+    float2 ss = block_sum2(ssv, sst, red);      // also orders the smem writes above
+    // ---- pass B (only with per-branch norms): scale branches in smem, total sum of squares ----
+    float total = ss.x + ss.y;
+    const bool vn = (P.flags & FRX_VISUAL_NORM) != 0, tn = (P.flags & FRX_TEXT_NORM) != 0 && P.dt > 0;
+    if (vn || tn) {
+      const float nv = vn ? sqrtf(ss.x) : 1.f, nt = tn ? sqrtf(ss.y) : 1.f;
+      float s2 = 0.f;
+      for (int c = tid * VEC; c < d; c += kFinThreads * VEC) {
+        typename V::T a = V::lds(row + c);
+        const bool is_v = c < P.dv;
+        if (is_v ? vn : tn) { V::div(a, is_v ? nv : nt); V::st(row + c, a); }   // own elements only
+        s2 += V::sq(a);
+      }
+      total = block_sum2(s2, 0.f, red).x;
+    }
+    // ---- pass C: smem -> global ----
+    const bool fn = (P.flags & FRX_FINAL_NORM) != 0;
+    const float nrm = sqrtf(total);
+    for (int c = tid * VEC; c < d; c += kFinThreads * VEC) {
+      typename V::T a = V::lds(row + c);
+      if (fn) V::div(a, nrm);
+      if (P.out_f32) V::st(P.out_f32 + p * d + c, a);
+      if (P.out_bf16) V::st_bf16(P.out_bf16 + p * P.ld_bf16 + c, a);
+    }
+    if (P.out_bf16) {
+      for (int64_t c = d + tid; c < P.ld_bf16; c += kFinThreads) P.out_bf16[p * P.ld_bf16 + c] = __float2bfloat16_rn(0.f);
+    }
+    __syncthreads();   // row[] is reused by the next post
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Brand embedding: out[i, :] = (1/A) sum_a W[ids[i], a] * E[a, :]   fp32 FMA, 64x64x16 smem tiles.
+// NB is at most ~10k and A = 2000, D <= 3072: at most 1.2e11 flop, a few ms once per evaluation.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBM = 64, kBN = 64, kBK = 16;
+
+__global__ void __launch_bounds__(256) brand_embed_kernel(const float* __restrict__ w, const float* __restrict__ e,
+                                                           const int64_t* __restrict__ ids, int nb, int a, int d,
+                                                           float* __restrict__ out) {
+  __shared__ float sw[kBK][kBM + 4];   // W tile, transposed: [k][m]
+  __shared__ float se[kBK][kBN + 4];   // E tile: [k][n]
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 4x4 outputs each
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < a; k0 += kBK) {
+    // W tile: 64 rows x 16 k -> 1024 elements / 256 threads = 4 each
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int idx = threadIdx.x + i * 256;
+      int m = idx >> 4, k = idx & 15;
+      float v = 0.f;
+      if (m0 + m < nb && k0 + k < a) {
+        int64_t r = ids ? ids[m0 + m] : (int64_t)(m0 + m);
+        v = __ldg(w + r * a + k0 + k);
+      }
+      sw[k][m] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int idx = threadIdx.x + i * 256;
+      int k = idx >> 6, n = idx & 63;
+      float v = 0.f;
+      if (k0 + k < a && n0 + n < d) v = __ldg(e + (int64_t)(k0 + k) * d + n0 + n);
+      se[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kBK; ++k) {
+      float wa[4], eb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) wa[i] = sw[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) eb[j] = se[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wa[i], eb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const float fa = (float)a;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < nb && n < d) out[(int64_t)m * d + n] = acc[i][j] / fa;   // .mean(0) = sum / A
+    }
+}
+
+}  // namespace frx
+
+extern "C" {
+
+int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_t* row_idx, const float* text,
+                       int64_t n_posts, int dv, int dt, int flags, float* out_f32, uint16_t* out_bf16,
+                       int64_t ld_bf16, void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(visual != nullptr && dv > 0, "frx_finalize_posts: visual is NULL or dv <= 0");
+  FRX_CHECK_ARG(n_posts >= 0 && dt >= 0, "frx_finalize_posts: negative size");
+  FRX_CHECK_ARG((dt == 0) == (text == nullptr), "frx_finalize_posts: text pointer and dt disagree");
+  FRX_CHECK_ARG(row_idx == nullptr || row_ptr != nullptr, "frx_finalize_posts: row_idx needs row_ptr");
+  FRX_CHECK_ARG(out_f32 || out_bf16, "frx_finalize_posts: no output requested");
+  const int d = dv + dt;
+  if (out_bf16) FRX_CHECK_ARG(ld_bf16 >= d && ld_bf16 % 8 == 0, "frx_finalize_posts: ld_bf16 must be >= dv+dt and a multiple of 8");
+  if (n_posts == 0) return FRX_OK;
+  const size_t smem = (size_t)d * sizeof(float);
+  FRX_CHECK_ARG(smem <= 200 * 1024, "frx_finalize_posts: dv+dt = %d exceeds the 51200-column row cache", d);
+  FinalizeParams P{visual, row_ptr, row_idx, text, n_posts, dv, dt, flags, out_f32,
+                   reinterpret_cast<__nv_bfloat16*>(out_bf16), ld_bf16};
+  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec = dv % 4 == 0 && dt % 4 == 0 && aligned16(visual) && aligned16(text) && aligned16(out_f32) &&
+                   aligned16(out_bf16);
+  int grid = (int)(n_posts < (int64_t)num_sms() * 8 ? n_posts : (int64_t)num_sms() * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec) {
+    if (smem > 48 * 1024) FRX_CUDA(cudaFuncSetAttribute(finalize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    finalize_kernel<4><<<grid, kFinThreads, smem, st>>>(P);
+  } else {
+    if (smem > 48 * 1024) FRX_CUDA(cudaFuncSetAttribute(finalize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    finalize_kernel<1><<<grid, kFinThreads, smem, st>>>(P);
+  }
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
+int frx_brand_embed(const float* w, int64_t w_rows, const float* e, const int64_t* brand_ids, int nb, int a, int d,
+                    float* out_f32, void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(w && e && out_f32, "frx_brand_embed: NULL pointer");
+  FRX_CHECK_ARG(nb >= 0 && a > 0 && d > 0, "frx_brand_embed: bad sizes nb=%d a=%d d=%d", nb, a, d);
+  FRX_CHECK_ARG(brand_ids != nullptr || nb <= w_rows, "frx_brand_embed: nb=%d exceeds table rows %lld", nb, (long long)w_rows);
+  if (nb == 0) return FRX_OK;
+  dim3 grid((d + kBN - 1) / kBN, (nb + kBM - 1) / kBM);
+  brand_embed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, e, brand_ids, nb, a, d, out_f32);
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,364 @@
+// A12 / A13: the in-batch similarity-tile losses, forward + backward (loss.py:87-143,
+// loss_ctrs.py:179-214).  fp32 end to end (the reference computes the tile in fp32); the B x B tile,
+// its rank weights, the hinge / soft-max terms and dS are produced on the device without the B GEMV
+// launches (loss.py:91-93), the four sorts (loss.py:96-105) or the B^2 host loop (loss.py:116-119) of
+// the reference.  Round-1 structure: a register-tiled fp32 GEMM + small fused row kernels; the
+// tensor-core (tf32 tcgen05) tile is the next step.
+#include "common.cuh"
+
+namespace frx {
+
+// ---------------------------------------------------------------------------------------------
+// C[M,N] = alpha * sum_k A(m,k) B(k,n) + beta * C,  A(m,k) = a[m*sam + k*sak], B(k,n) = b[k*sbk + n*sbn]
+// 64x64x16 tiles, 256 threads, 4x4 outputs per thread.
+// ---------------------------------------------------------------------------------------------
+constexpr int GM = 64, GN = 64, GK = 16;
+
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ a, int64_t sam, int64_t sak,
+                                                     const float* __restrict__ b, int64_t sbk, int64_t sbn,
+                                                     float* __restrict__ c, int64_t ldc, int m, int n, int k,
+                                                     float alpha, float beta) {
+  __shared__ float sa[GK][GM + 4];
+  __shared__ float sb[GK][GN + 4];
+  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const bool a_kfast = sak == 1, b_kfast = sbk == 1;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < k; k0 += GK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      int mm, kk;
+      if (a_kfast) { mm = idx >> 4; kk = idx & 15; } else { kk = idx >> 6; mm = idx & 63; }
+      float v = 0.f;
+      if (m0 + mm < m && k0 + kk < k) v = __ldg(a + (int64_t)(m0 + mm) * sam + (int64_t)(k0 + kk) * sak);
+      sa[kk][mm] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      int nn, kk;
+      if (b_kfast) { nn = idx >> 4; kk = idx & 15; } else { kk = idx >> 6; nn = idx & 63; }
+      float v = 0.f;
+      if (n0 + nn < n && k0 + kk < k) v = __ldg(b + (int64_t)(k0 + kk) * sbk + (int64_t)(n0 + nn) * sbn);
+      sb[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = sa[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = sb[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int mm = m0 + ty * 4 + i, nn = n0 + tx * 4 + j;
+      if (mm < m && nn < n) {
+        float* dst = c + (int64_t)mm * ldc + nn;
+        *dst = beta == 0.f ? alpha * acc[i][j] : alpha * acc[i][j] + beta * *dst;
+      }
+    }
+}
+
+static void sgemm(cudaStream_t st, const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbk, int64_t sbn,
+                  float* c, int64_t ldc, int m, int n, int k, float alpha, float beta) {
+  dim3 grid((n + GN - 1) / GN, (m + GM - 1) / GM);
+  sgemm_kernel<<<grid, 256, 0, st>>>(a, sam, sak, b, sbk, sbn, c, ldc, m, n, k, alpha, beta);
+}
+
+// ---------------------------------------------------------------------------------------------
+// rank weights of the diagonal (loss.py:96-105): block i counts, in row i and in column i, the entries
+// that precede S[i,i] in a descending sort (ties: smaller index first).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_sum_int(int v, int* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int t = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+  return t;
+}
+__device__ __forceinline__ float block_sum_float(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(128) tile_rank_kernel(const float* __restrict__ s, int b, float* __restrict__ rank_p,
+                                                         float* __restrict__ rank_b, float* __restrict__ diag) {
+  __shared__ int red[4];
+  const int i = blockIdx.x;
+  const float d = s[(int64_t)i * b + i];
+  int cr = 0, cc = 0;
+  for (int j = threadIdx.x; j < b; j += blockDim.x) {
+    const float r = s[(int64_t)i * b + j], c = s[(int64_t)j * b + i];
+    cr += (r > d) || (r == d && j < i);
+    cc += (c > d) || (c == d && j < i);
+  }
+  cr = block_sum_int(cr, red);
+  cc = block_sum_int(cc, red);
+  if (threadIdx.x == 0) {
+    const float fb = (float)b;
+    rank_p[i] = 1.0f / (fb - (float)(cr + 1) + 1.0f) + 1.0f;
+    rank_b[i] = 1.0f / (fb - (float)(cc + 1) + 1.0f) + 1.0f;
+    diag[i] = d;
+  }
+}
+
+// hinge + same-brand mask + column-broadcast weights (loss.py:107-132), loss partials and dS.
+__global__ void __launch_bounds__(256) triplet_row_kernel(const float* __restrict__ s, const int64_t* __restrict__ ids, int b,
+                                                           float margin, float scale, const float* __restrict__ rank_p,
+                                                           const float* __restrict__ rank_b, const float* __restrict__ diag,
+                                                           float* __restrict__ ds, float* __restrict__ partial) {
+  __shared__ float redf[8];
+  __shared__ int redi[8];
+  const int i = blockIdx.x;
+  const float di = diag[i];
+  const int64_t idi = ids[i];
+  float loss = 0.f, row_gp = 0.f;
+  int col_cnt = 0;
+  for (int j = threadIdx.x; j < b; j += blockDim.x) {
+    const bool same = ids[j] == idi;
+    const float sij = s[(int64_t)i * b + j];
+    const float xp = margin + sij - di;         // cost_p argument (d1 = S[i,i])
+    const float xb = margin + sij - diag[j];    // cost_b argument (d2 = S[j,j])
+    float g = 0.f;
+    if (!same) {
+      const float wp = rank_p[j], wb = rank_b[j];
+      loss += fmaxf(xp, 0.f) * wp + fmaxf(xb, 0.f) * wb;
+      if (xp >= 0.f) { g += wp; row_gp += wp; }   // torch.clamp backward passes the gradient at x == min
+      if (xb >= 0.f) g += wb;
+    }
+    if (j != i) ds[(int64_t)i * b + j] = scale * g;
+    // column i: entries (j, i) whose cost_b argument margin + S[j,i] - S[i,i] is active
+    const float xcol = margin + s[(int64_t)j * b + i] - di;
+    col_cnt += (!same && xcol >= 0.f) ? 1 : 0;
+  }
+  loss = block_sum_float(loss, redf);
+  row_gp = block_sum_float(row_gp, redf);
+  col_cnt = block_sum_int(col_cnt, redi);
+  if (threadIdx.x == 0) {
+    partial[i] = loss;
+    ds[(int64_t)i * b + i] = -scale * (row_gp + rank_b[i] * (float)col_cnt);
+  }
+}
+
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int n, float scale,
+                                                               float* __restrict__ out) {
+  __shared__ double red[8];
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += (double)partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    out[0] = (float)(t * (double)scale);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// contrastive pieces
+// ---------------------------------------------------------------------------------------------
+// F.normalize: y = x / max(||x||, 1e-12); norm_out optional.
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __restrict__ x, int d, float* __restrict__ y,
+                                                              float* __restrict__ norm_out) {
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) { const float v = x[(int64_t)r * d + c]; ss += v * v; }
+  ss = block_sum_float(ss, red);
+  const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) y[(int64_t)r * d + c] = x[(int64_t)r * d + c] / nrm;
+  if (norm_out && threadIdx.x == 0) norm_out[r] = nrm;
+}
+
+// dx = (dy - y * <y, dy>) / norm   (backward of F.normalize away from the eps clamp)
+__global__ void __launch_bounds__(256) normalize_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                             const float* __restrict__ nrm, int d, float* __restrict__ dx) {
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) dot += dy[(int64_t)r * d + c] * y[(int64_t)r * d + c];
+  dot = block_sum_float(dot, red);
+  const float n = nrm[r];
+  for (int c = threadIdx.x; c < d; c += blockDim.x)
+    dx[(int64_t)r * d + c] = (dy[(int64_t)r * d + c] - y[(int64_t)r * d + c] * dot) / n;
+}
+
+// Row i of the cross-modal soft-max (loss_ctrs.py:166-177), in place:
+//   inter[i,:] (already / T)  -> d loss / d inter[i,:]
+//   ori[i,:]   (raw dots)     -> d loss / d ori[i,:]   (mask and 1/T folded in)
+__global__ void __launch_bounds__(256) contrastive_row_kernel(float* __restrict__ inter, float* __restrict__ ori, int b,
+                                                               int n_keys, int mask_col0, int no_intra, float inv_t,
+                                                               float neg_w, float scale, const float* __restrict__ weight,
+                                                               float* __restrict__ partial) {
+  __shared__ float red[8];
+  const int i = blockIdx.x;
+  float* irow = inter + (int64_t)i * b;
+  float* orow = ori + (int64_t)i * n_keys;
+  const int mcol = mask_col0 + i;
+  float se = 0.f, sq = 0.f;
+  for (int j = threadIdx.x; j < b; j += blockDim.x) se += expf(irow[j]);
+  for (int q = threadIdx.x; q < n_keys; q += blockDim.x) {
+    const float logit = (no_intra || q == mcol) ? 0.f : orow[q] * inv_t;   // masked logit is 0 -> exp = 1
+    sq += expf(logit);
+  }
+  se = block_sum_float(se, red);
+  sq = block_sum_float(sq, red);
+  const float z = se + neg_w * sq;
+  const float w = weight[i];
+  const float dii = irow[i];
+  __syncthreads();
+  for (int j = threadIdx.x; j < b; j += blockDim.x) {
+    float g = scale * w * (expf(irow[j]) / z);
+    if (j == i) g -= scale * w;
+    irow[j] = g;
+  }
+  for (int q = threadIdx.x; q < n_keys; q += blockDim.x) {
+    float g = 0.f;
+    if (!no_intra && q != mcol) g = scale * w * neg_w * expf(orow[q] * inv_t) / z * inv_t;
+    orow[q] = g;
+  }
+  if (threadIdx.x == 0) partial[i] = -logf(expf(dii) / z) * w;
+}
+
+struct TripletWs { float *s, *ds, *rank_p, *rank_b, *diag, *partial; };
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace frx
+
+extern "C" {
+
+size_t frx_triplet_workspace_bytes(int b, int d) {
+  (void)d;
+  if (b <= 0) return 0;
+  return 2 * frx::align256((size_t)b * b * 4) + 4 * frx::align256((size_t)b * 4) + 256;
+}
+
+int frx_triplet_fwd_bwd(const int64_t* brand_ids, const float* brand, const float* post, int b, int d, float margin,
+                        int mean_style, float* loss, float* d_brand, float* d_post, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(brand_ids && brand && post && loss, "frx_triplet_fwd_bwd: NULL pointer");
+  FRX_CHECK_ARG(b > 0 && d > 0, "frx_triplet_fwd_bwd: bad sizes");
+  FRX_CHECK_ARG((d_brand == nullptr) == (d_post == nullptr), "frx_triplet_fwd_bwd: gradients go together");
+  if (!workspace || workspace_bytes < frx_triplet_workspace_bytes(b, d)) {
+    set_error("frx_triplet_fwd_bwd: workspace %zu bytes, need %zu", workspace_bytes, frx_triplet_workspace_bytes(b, d));
+    return FRX_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+  float* s = reinterpret_cast<float*>(w); w += align256((size_t)b * b * 4);
+  float* ds = reinterpret_cast<float*>(w); w += align256((size_t)b * b * 4);
+  float* rank_p = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
+  float* rank_b = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
+  float* diag = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
+  float* partial = reinterpret_cast<float*>(w);
+  const float scale = mean_style ? 1.0f / ((float)b * (float)b) : 1.0f;
+  // S[i,j] = post_i . brand_j   (loss.py:91-93)
+  sgemm(st, post, d, 1, brand, 1, d, s, b, b, b, d, 1.f, 0.f);
+  tile_rank_kernel<<<b, 128, 0, st>>>(s, b, rank_p, rank_b, diag);
+  triplet_row_kernel<<<b, 256, 0, st>>>(s, brand_ids, b, margin, scale, rank_p, rank_b, diag, ds, partial);
+  reduce_partials_kernel<<<1, 256, 0, st>>>(partial, b, scale, loss);
+  if (d_post) {
+    sgemm(st, ds, b, 1, brand, d, 1, d_post, d, b, d, b, 1.f, 0.f);     // dPost  = dS   . brand
+    sgemm(st, ds, 1, b, post, d, 1, d_brand, d, b, d, b, 1.f, 0.f);     // dBrand = dS^T . post
+  }
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
+size_t frx_contrastive_workspace_bytes(int b, int d, int n_keys) {
+  if (b <= 0 || d <= 0) return 0;
+  const int nk = n_keys > 0 ? n_keys : b;
+  return frx::align256((size_t)b * b * 4) + frx::align256((size_t)b * nk * 4) + 4 * frx::align256((size_t)b * d * 4) +
+         6 * frx::align256((size_t)b * 4) + 256;
+}
+
+int frx_contrastive_fwd_bwd(const float* brand, const float* post, int b, int d, const float* keys, int n_keys,
+                            int mask_col0, int no_intra, float temperature, float negative_weight, int mean_style,
+                            float* loss, float* d_brand, float* d_post, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(brand && post && loss, "frx_contrastive_fwd_bwd: NULL pointer");
+  FRX_CHECK_ARG(b > 0 && d > 0, "frx_contrastive_fwd_bwd: bad sizes");
+  FRX_CHECK_ARG((keys == nullptr) == (n_keys == 0), "frx_contrastive_fwd_bwd: keys and n_keys disagree");
+  FRX_CHECK_ARG((d_brand == nullptr) == (d_post == nullptr), "frx_contrastive_fwd_bwd: gradients go together");
+  const int nk = keys ? n_keys : b;
+  FRX_CHECK_ARG(mask_col0 >= 0 && mask_col0 + b <= nk, "frx_contrastive_fwd_bwd: mask columns %d..%d outside %d keys",
+                mask_col0, mask_col0 + b - 1, nk);
+  const size_t need = frx_contrastive_workspace_bytes(b, d, n_keys);
+  if (!workspace || workspace_bytes < need) {
+    set_error("frx_contrastive_fwd_bwd: workspace %zu bytes, need %zu", workspace_bytes, need);
+    return FRX_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+  float* inter = reinterpret_cast<float*>(w); w += align256((size_t)b * b * 4);
+  float* ori = reinterpret_cast<float*>(w); w += align256((size_t)b * nk * 4);
+  float* bn = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
+  float* pn = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
+  float* dbn = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
+  float* dpn = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
+  float* weight = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
+  float* rank_b = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
+  float* diag = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
+  float* partial = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
+  float* nrm_b = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
+  float* nrm_p = reinterpret_cast<float*>(w);
+  const float inv_t = 1.0f / temperature;
+  const float scale = mean_style ? 1.0f / (float)b : 1.0f;
+  // rank weight from the RAW tile (loss_ctrs.py:182-192)
+  sgemm(st, post, d, 1, brand, 1, d, inter, b, b, b, d, 1.f, 0.f);
+  tile_rank_kernel<<<b, 128, 0, st>>>(inter, b, weight, rank_b, diag);
+  normalize_rows_kernel<<<b, 256, 0, st>>>(brand, d, bn, nrm_b);
+  normalize_rows_kernel<<<b, 256, 0, st>>>(post, d, pn, nrm_p);
+  const float* kk = keys ? keys : pn;
+  // inter[i,j] = bn_i . pn_j / T ; ori[i,q] = pn_i . key_q
+  sgemm(st, bn, d, 1, pn, 1, d, inter, b, b, b, d, inv_t, 0.f);
+  sgemm(st, pn, d, 1, kk, 1, d, ori, nk, b, nk, d, 1.f, 0.f);
+  contrastive_row_kernel<<<b, 256, 0, st>>>(inter, ori, b, nk, mask_col0, no_intra, inv_t, negative_weight, scale,
+                                            weight, partial);
+  reduce_partials_kernel<<<1, 256, 0, st>>>(partial, b, scale, loss);
+  if (d_post) {
+    sgemm(st, inter, b, 1, pn, d, 1, dbn, d, b, d, b, inv_t, 0.f);       // d_bn  = dInter   . pn / T
+    sgemm(st, inter, 1, b, bn, d, 1, dpn, d, b, d, b, inv_t, 0.f);       // d_pn  = dInter^T . bn / T
+    if (!no_intra) {
+      sgemm(st, ori, nk, 1, kk, d, 1, dpn, d, b, d, nk, 1.f, 1.f);       //       + G . keys
+      if (!keys) sgemm(st, ori, 1, nk, pn, d, 1, dpn, d, b, d, b, 1.f, 1.f);   // + G^T . pn (keys = pn carry grad)
+    }
+    normalize_bwd_kernel<<<b, 256, 0, st>>>(dbn, bn, nrm_b, d, d_brand);
+    normalize_bwd_kernel<<<b, 256, 0, st>>>(dpn, pn, nrm_p, d, d_post);
+  }
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
+int frx_normalize_rows(const float* x, int rows, int d, float* out, void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(x && out && rows > 0 && d > 0, "frx_normalize_rows: bad arguments");
+  normalize_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, d, out, nullptr);
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
+}  // extern "C"

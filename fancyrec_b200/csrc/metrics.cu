@@ -1,0 +1,288 @@
+// A6-A9: integer rank statistics behind AUC / NDCG@k / recall@k / MedR (evaluator.py:103-143,
+// util/ndcg.py).  Everything here is HBM/latency-bound integer work on warp-level primitives; the
+// float64 metric values are computed from these integers on the host exactly as the reference does.
+#include "common.cuh"
+
+namespace frx {
+
+// n_pos[b] and the best positive per brand as a packed (score, ~index) key (atomicMax).
+__global__ void label_stats_kernel(const int32_t* __restrict__ labels, const float* __restrict__ pos_score,
+                                   int64_t n_posts, int nb, int64_t index_base, int32_t* __restrict__ n_pos,
+                                   unsigned long long* __restrict__ best_key) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_posts; j += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t b = labels[j];
+    if (b >= 0 && b < nb) {
+      atomicAdd(n_pos + b, 1);
+      atomicMax(best_key + b, make_key(pos_score[j], (uint32_t)(index_base + j)));
+    }
+  }
+}
+
+__global__ void decode_best_kernel(const unsigned long long* __restrict__ best_key, const int32_t* __restrict__ n_pos,
+                                   int nb, float* __restrict__ best_score, int32_t* __restrict__ best_index) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  if (n_pos[b] > 0) {
+    best_score[b] = key_score(best_key[b]);
+    best_index[b] = (int32_t)key_index(best_key[b]);
+  } else {
+    best_score[b] = -INFINITY;
+    best_index[b] = -1;
+  }
+}
+
+// One warp per brand: relevance bits of the first 64 ranks + rank of the first positive in the list.
+__global__ void rank_from_topk_kernel(const int32_t* __restrict__ topk_index, int nb, int k,
+                                      const int32_t* __restrict__ labels, int64_t n_posts, int64_t index_base,
+                                      unsigned long long* __restrict__ hit_mask, int32_t* __restrict__ first_rank) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= nb) return;
+  unsigned long long mask = 0ull;
+  int first = -1;
+  for (int base = 0; base < k; base += 32) {
+    const int r = base + lane;
+    bool hit = false;
+    if (r < k) {
+      const int64_t local = (int64_t)topk_index[(size_t)b * k + r] - index_base;
+      if (topk_index[(size_t)b * k + r] >= 0 && local >= 0 && local < n_posts) hit = labels[local] == b;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+    if (base < 64) mask |= (unsigned long long)m << base;
+    if (first < 0 && m) first = base + __ffs(m) - 1;
+    if (first >= 0 && base >= 32) break;   // bits 0..63 and the first hit are all we need
+  }
+  if (lane == 0) { hit_mask[b] = mask; first_rank[b] = first; }
+}
+
+// ---- positives grouped by brand, ascending --------------------------------------------------
+__global__ void seg_scan_kernel(const int32_t* __restrict__ n_pos, int nb, int64_t* __restrict__ seg_ptr,
+                                unsigned long long* __restrict__ cursor) {
+  // single block; nb is at most a few 10^4
+  __shared__ long long carry;
+  __shared__ long long wsum[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += blockDim.x) {
+    const int b = base + threadIdx.x;
+    long long v = b < nb ? (long long)n_pos[b] : 0;
+    long long incl = v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      long long w = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0, wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        long long t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      wsum[lane] = wi - w;   // exclusive
+    }
+    __syncthreads();
+    const long long excl = carry + wsum[warp] + incl - v;
+    if (b < nb) { seg_ptr[b] = excl; cursor[b] = 0ull; }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) seg_ptr[nb] = carry;
+}
+
+__global__ void scatter_pos_kernel(const int32_t* __restrict__ labels, const float* __restrict__ pos_score,
+                                   int64_t n_posts, int nb, const int64_t* __restrict__ seg_ptr,
+                                   unsigned long long* __restrict__ cursor, float* __restrict__ pos_sorted) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_posts; j += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t b = labels[j];
+    if (b >= 0 && b < nb) {
+      const unsigned long long slot = atomicAdd(cursor + b, 1ull);
+      pos_sorted[seg_ptr[b] + (int64_t)slot] = pos_score[j];
+    }
+  }
+}
+
+// One block per brand: ascending bitonic sort of its positives (smem when they fit, else in place in
+// global memory -- correct, slower, only for brands with > 32768 positives).
+constexpr int kSortSmemFloats = 32768;
+__global__ void __launch_bounds__(256) sort_segments_kernel(const int64_t* __restrict__ seg_ptr, float* __restrict__ pos_sorted) {
+  extern __shared__ float sbuf[];
+  const int b = blockIdx.x;
+  const int64_t s0 = seg_ptr[b];
+  const int64_t n = seg_ptr[b + 1] - s0;
+  if (n <= 1) return;
+  int64_t np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  float* g = pos_sorted + s0;
+  const bool in_smem = np2 <= kSortSmemFloats;
+  if (in_smem) {
+    for (int64_t i = threadIdx.x; i < np2; i += blockDim.x) sbuf[i] = i < n ? g[i] : INFINITY;
+  }
+  for (int64_t size = 2; size <= np2; size <<= 1) {
+    for (int64_t stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int64_t t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+        const int64_t lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int64_t hi = lo + stride;
+        const bool asc = ((lo & size) == 0);
+        if (in_smem) {
+          const float a = sbuf[lo], c = sbuf[hi];
+          if ((a > c) == asc) { sbuf[lo] = c; sbuf[hi] = a; }
+        } else {
+          // virtual +inf padding beyond n
+          const float a = lo < n ? g[lo] : INFINITY, c = hi < n ? g[hi] : INFINITY;
+          if ((a > c) == asc) {
+            if (lo < n) g[lo] = c;
+            if (hi < n) g[hi] = a;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (in_smem)
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) g[i] = sbuf[i];
+}
+
+// ---- exact AUC numerator + "posts before the first positive" from dense score rows ---------
+constexpr int kAucChunk = 8192;   // positives staged in shared memory per sweep (32 KB)
+
+__global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__ scores, int64_t ld, int row0,
+                                                       int64_t n_posts, const int32_t* __restrict__ labels,
+                                                       const int64_t* __restrict__ seg_ptr,
+                                                       const float* __restrict__ pos_sorted,
+                                                       const float* __restrict__ best_score,
+                                                       const int32_t* __restrict__ best_index, int64_t index_base,
+                                                       unsigned long long* __restrict__ auc_num,
+                                                       unsigned long long* __restrict__ before_first) {
+  __shared__ float spos[kAucChunk];
+  __shared__ unsigned long long red[2][8];
+  const int r = blockIdx.x;
+  const int b = row0 + r;
+  const int64_t c0 = n_posts * blockIdx.y / gridDim.y, c1 = n_posts * (blockIdx.y + 1) / gridDim.y;
+  const int64_t p0 = seg_ptr[b], np = seg_ptr[b + 1] - p0;
+  if (np == 0) return;
+  const float bs = best_score[b];
+  const int64_t bi = best_index[b];
+  const float* row = scores + (int64_t)r * ld;
+  unsigned long long auc = 0ull, before = 0ull;
+  for (int64_t ch = 0; ch < np; ch += kAucChunk) {
+    const int m = (int)((np - ch) < kAucChunk ? (np - ch) : kAucChunk);
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) spos[i] = pos_sorted[p0 + ch + i];
+    __syncthreads();
+    for (int64_t j = c0 + threadIdx.x; j < c1; j += blockDim.x) {
+      const float s = row[j];
+      if (ch == 0) before += ((s > bs) || (s == bs && (index_base + j) < bi)) ? 1ull : 0ull;
+      if (labels[j] == b) continue;          // negatives only (evaluator.py:112)
+      // number of positives e in this chunk with e > s  ==  m - upper_bound(spos, s)
+      int lo = 0, hi = m;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (spos[mid] > s) hi = mid; else lo = mid + 1;
+      }
+      auc += (unsigned long long)(m - lo);
+    }
+  }
+  // block reduce
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    auc += __shfl_xor_sync(0xffffffffu, auc, o);
+    before += __shfl_xor_sync(0xffffffffu, before, o);
+  }
+  if (lane == 0) { red[0][warp] = auc; red[1][warp] = before; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long a = 0, c = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += red[0][w]; c += red[1][w]; }
+    if (a) atomicAdd(auc_num + b, a);
+    if (c) atomicAdd(before_first + b, c);
+  }
+}
+
+}  // namespace frx
+
+extern "C" {
+
+int frx_label_stats(const int32_t* labels, const float* pos_score, int64_t n_posts, int nb, int64_t index_base,
+                    int32_t* n_pos, float* best_score, int32_t* best_index, void* workspace_nb_u64, void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(labels && pos_score && n_pos && best_score && best_index && workspace_nb_u64, "frx_label_stats: NULL pointer");
+  FRX_CHECK_ARG(nb > 0 && n_posts >= 0, "frx_label_stats: bad sizes");
+  FRX_CHECK_ARG(index_base >= 0 && index_base + n_posts <= 2147483647LL, "frx_label_stats: index range must fit int32");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(workspace_nb_u64);
+  FRX_CUDA(cudaMemsetAsync(n_pos, 0, (size_t)nb * sizeof(int32_t), st));
+  FRX_CUDA(cudaMemsetAsync(keys, 0, (size_t)nb * sizeof(unsigned long long), st));
+  if (n_posts > 0) {
+    int64_t blocks = (n_posts + 255) / 256;
+    const int64_t maxb = (int64_t)num_sms() * 16;
+    if (blocks > maxb) blocks = maxb;
+    label_stats_kernel<<<(int)blocks, 256, 0, st>>>(labels, pos_score, n_posts, nb, index_base, n_pos, keys);
+    FRX_LAUNCH_CHECK();
+  }
+  decode_best_kernel<<<(nb + 255) / 256, 256, 0, st>>>(keys, n_pos, nb, best_score, best_index);
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
+int frx_rank_from_topk(const int32_t* topk_index, int nb, int k, const int32_t* labels, int64_t n_posts,
+                       int64_t index_base, unsigned long long* hit_mask, int32_t* first_rank, void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(topk_index && labels && hit_mask && first_rank, "frx_rank_from_topk: NULL pointer");
+  FRX_CHECK_ARG(nb > 0 && k > 0, "frx_rank_from_topk: bad sizes");
+  const int warps_per_block = 8;
+  rank_from_topk_kernel<<<(nb + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, (cudaStream_t)stream>>>(
+      topk_index, nb, k, labels, n_posts, index_base, hit_mask, first_rank);
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
+int frx_group_positives(const int32_t* labels, const float* pos_score, int64_t n_posts, int nb, const int32_t* n_pos,
+                        int64_t* seg_ptr, float* pos_sorted, void* workspace_nb_i64, void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(labels && pos_score && n_pos && seg_ptr && pos_sorted && workspace_nb_i64, "frx_group_positives: NULL pointer");
+  FRX_CHECK_ARG(nb > 0 && n_posts >= 0, "frx_group_positives: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* cursor = reinterpret_cast<unsigned long long*>(workspace_nb_i64);
+  seg_scan_kernel<<<1, 1024, 0, st>>>(n_pos, nb, seg_ptr, cursor);
+  FRX_LAUNCH_CHECK();
+  if (n_posts > 0) {
+    int64_t blocks = (n_posts + 255) / 256;
+    const int64_t maxb = (int64_t)num_sms() * 16;
+    if (blocks > maxb) blocks = maxb;
+    scatter_pos_kernel<<<(int)blocks, 256, 0, st>>>(labels, pos_score, n_posts, nb, seg_ptr, cursor, pos_sorted);
+    FRX_LAUNCH_CHECK();
+    const size_t smem = (size_t)kSortSmemFloats * sizeof(float);
+    FRX_CUDA(cudaFuncSetAttribute(sort_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sort_segments_kernel<<<nb, 256, smem, st>>>(seg_ptr, pos_sorted);
+    FRX_LAUNCH_CHECK();
+  }
+  return FRX_OK;
+}
+
+int frx_auc_rows(const float* scores, int64_t ld, int row0, int n_rows, int64_t n_posts, const int32_t* labels,
+                 const int64_t* seg_ptr, const float* pos_sorted, const float* best_score, const int32_t* best_index,
+                 int64_t index_base, unsigned long long* auc_num, unsigned long long* before_first, void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(scores && labels && seg_ptr && pos_sorted && best_score && best_index && auc_num && before_first,
+                "frx_auc_rows: NULL pointer");
+  FRX_CHECK_ARG(n_rows > 0 && n_posts > 0 && ld >= n_posts && row0 >= 0, "frx_auc_rows: bad sizes");
+  int64_t ysplit = ((int64_t)num_sms() * 4 + n_rows - 1) / n_rows;
+  const int64_t max_split = (n_posts + 4095) / 4096;
+  if (ysplit > max_split) ysplit = max_split;
+  if (ysplit < 1) ysplit = 1;
+  if (ysplit > 65535) ysplit = 65535;
+  dim3 grid(n_rows, (unsigned)ysplit);
+  auc_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(scores, ld, row0, n_posts, labels, seg_ptr, pos_sorted,
+                                                          best_score, best_index, index_base, auc_num, before_first);
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
+}  // extern "C"

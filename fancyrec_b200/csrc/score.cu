@@ -1,0 +1,655 @@
+// A5 + A6: brand x post cosine-score contraction on the 5th-gen tensor cores with the per-brand
+// top-k selection fused into the GEMM epilogue (the score matrix is never written).
+//
+// Replaces cal_sim's im.mm(s.t()) (evaluator.py:29), the device->host copy of the full score matrix
+// (evaluator.py:96) and the per-brand sorted()/np.argsort (evaluator.py:108-109,124).
+//
+// Shape of the kernel (one persistent CTA per SM, warp-specialised):
+//   warp 0 (one lane)  TMA producer: A = 128 brands x 64 k, B = 256 posts x 64 k (bf16, SWIZZLE_128B)
+//                      into a 4-stage shared-memory ring (48 KB / stage)
+//   warp 1 (one lane)  tcgen05.mma issuer: M=128, N=256, K=16 per instruction, fp32 accumulators in
+//                      TMEM, two accumulator stages (2 x 256 columns = all 512 TMEM columns) so the
+//                      epilogue of tile t overlaps the main loop of tile t+1
+//   warp 2             TMEM alloc / dealloc
+//   warps 4-7          epilogue: thread = TMEM lane = one brand row.  Modes:
+//       TOPK   per-row running threshold in a register; a score >= threshold is appended (rare after
+//              warm-up) as a packed 64-bit (score, ~index) key to the row's private candidate buffer;
+//              a full buffer is compacted warp-cooperatively by an MSB-first radix select that raises
+//              the threshold.  Also extracts S[label[j], j] (the positive's score) for the metric side.
+//       DENSE  writes the fp32 tile (score-tolerance tests, AUC row sweep).
+//       COUNT  counts, per row, the scores that precede a given (score, index) threshold
+//              (= rank of the first positive, evaluator.py:116) without materialising anything.
+// A work item is (m_tile, split): 128 brand rows x a contiguous range of 256-post tiles.  Items are
+// numbered split-major so that the CTAs resident at any time read the same post range (served by L2).
+// Per-item candidate lists are merged by merge_partials_kernel (bitonic sort of <= 16384 keys in smem).
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace frx {
+using namespace sm100;
+
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;                 // warps 4..7 -> TMEM lane quarters 0..3
+constexpr int TMEM_COLS = 512;
+constexpr int MAX_MERGE_KEYS = 16384;
+
+enum Mode { MODE_TOPK = 0, MODE_DENSE = 1, MODE_COUNT = 2 };
+
+struct ScoreParams {
+  int nb;
+  int64_t n_posts;
+  int num_k_blocks, num_m_tiles, splits;
+  int64_t num_n_tiles;
+  int64_t index_base;
+  // TOPK
+  int k, cap, keep_limit;
+  unsigned long long* part_keys;   // [items][128][cap]
+  int* part_cnt;                   // [items][128]
+  const int32_t* labels;
+  float* pos_score;
+  // DENSE
+  float* dense;
+  int64_t ld_dense;
+  // COUNT
+  const float* thr_score;
+  const int32_t* thr_index;
+  unsigned long long* count_out;
+};
+
+struct SmemTail {
+  uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+  uint32_t hist[4][256];
+};
+constexpr size_t SMEM_BYTES = 1024 /* alignment slack */ + (size_t)STAGES * STAGE_BYTES + sizeof(SmemTail);
+
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative radix select on one row's candidate buffer (global memory, L2-resident).
+// Keeps the best `k` keys (or, when !exact, between k and keep_limit keys as soon as a digit boundary
+// allows it), compacts them to buf[0..kept) and returns kept; *thr_out = a score that every kept key
+// reaches and no dropped key exceeds (the new append threshold).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_select(unsigned long long* buf, int n, int k, int keep_limit, bool exact,
+                                           uint32_t* hist, float* thr_out) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long prefix = 0;
+  int need = k, above_total = 0, shift = 56, bucket = 0;
+  for (int pass = 0; pass < 8; ++pass, shift -= 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hist[lane * 8 + i] = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      unsigned long long key = __ldcg(buf + i);
+      if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
+    }
+    __syncwarp();
+    uint32_t h[8], lsum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { h[i] = hist[lane * 8 + i]; lsum += h[i]; }
+    // inclusive suffix sum over lanes (higher lane = higher digits)
+    uint32_t suf = lsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_down_sync(0xffffffffu, suf, o);
+      if (lane + o < 32) suf += t;
+    }
+    const bool cross = suf >= (uint32_t)need && (suf - lsum) < (uint32_t)need;
+    const uint32_t cm = __ballot_sync(0xffffffffu, cross);
+    const int cl = __ffs(cm) - 1;            // exactly one lane crosses (need <= matching count)
+    int digit = 0, above = 0, bcnt = 0;
+    if (lane == cl) {
+      uint32_t acc = suf - lsum;             // matching keys in higher lanes
+#pragma unroll
+      for (int i = 7; i >= 0; --i) {
+        if (bcnt == 0) {
+          if (acc + h[i] >= (uint32_t)need) { digit = lane * 8 + i; above = (int)acc; bcnt = (int)h[i]; }
+          else acc += h[i];
+        }
+      }
+    }
+    digit = __shfl_sync(0xffffffffu, digit, cl);
+    above = __shfl_sync(0xffffffffu, above, cl);
+    bucket = __shfl_sync(0xffffffffu, bcnt, cl);
+    above_total += above;
+    need -= above;
+    prefix = (prefix << 8) | (unsigned long long)digit;
+    if (!exact && above_total + bucket <= keep_limit) { break; }
+    if (pass == 7) break;
+  }
+  if (shift < 0) shift = 0;
+  const unsigned long long thr_key = prefix << shift;   // smallest key of the boundary bucket
+  int out = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    unsigned long long key = i < n ? __ldcg(buf + i) : 0ull;
+    const bool keep = i < n && key >= thr_key;
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (keep) buf[out + __popc(m & ((1u << lane) - 1u))] = key;
+    out += __popc(m);
+    __syncwarp();
+  }
+  float t = ordered_to_score((uint32_t)(thr_key >> 32));
+  if (t != t) t = -INFINITY;   // bucket edge decoded to a NaN pattern
+  *thr_out = t;
+  return out;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+             const ScoreParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;            // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw);
+  SmemTail* tail = reinterpret_cast<SmemTail*>(smem + (size_t)STAGES * STAGE_BYTES);
+  const uint32_t smem_a = base, smem_b = base + STAGES * A_STAGE_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&tail->full[s]), 1); mbar_init(smem_u32(&tail->empty[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tail->tmem_full[s]), 1); mbar_init(smem_u32(&tail->tmem_empty[s]), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(&tail->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  const int n_items = P.num_m_tiles * P.splits;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int m_tile = item % P.num_m_tiles, split = item / P.num_m_tiles;
+        const int64_t t0 = P.num_n_tiles * split / P.splits, t1 = P.num_n_tiles * (split + 1) / P.splits;
+        for (int64_t t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < P.num_k_blocks; ++kb) {
+            mbar_wait(smem_u32(&tail->empty[stage]), phase ^ 1);
+            const uint32_t fb = smem_u32(&tail->full[stage]);
+            mbar_arrive_expect_tx(fb, STAGE_BYTES);
+            tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, fb, kb * BK, m_tile * BM);
+            tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, fb, kb * BK, (int32_t)(t * BN));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int split = item / P.num_m_tiles;
+        const int64_t t0 = P.num_n_tiles * split / P.splits, t1 = P.num_n_tiles * (split + 1) / P.splits;
+        for (int64_t t = t0; t < t1; ++t) {
+          mbar_wait(smem_u32(&tail->tmem_empty[as]), aphase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * BN;
+          for (int kb = 0; kb < P.num_k_blocks; ++kb) {
+            mbar_wait(smem_u32(&tail->full[stage]), phase);
+            tc_fence_after();
+            const uint64_t da = make_sw128_kmajor_desc(smem_a + stage * A_STAGE_BYTES);
+            const uint64_t db = make_sw128_kmajor_desc(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
+              umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            }
+            umma_commit(smem_u32(&tail->empty[stage]));        // frees the smem slot when the MMAs retire
+            if (kb == P.num_k_blocks - 1) umma_commit(smem_u32(&tail->tmem_full[as]));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // =========================== epilogue ===========================
+    const int q = warp - EPI_WARP0;                  // TMEM lane quarter (== warp % 4)
+    const int row_in_tile = q * 32 + lane;
+    uint32_t* hist = tail->hist[q];
+    int as = 0; uint32_t aphase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int m_tile = item % P.num_m_tiles, split = item / P.num_m_tiles;
+      const int64_t t0 = P.num_n_tiles * split / P.splits, t1 = P.num_n_tiles * (split + 1) / P.splits;
+      const int row = m_tile * BM + row_in_tile;
+      const bool row_ok = row < P.nb;
+
+      // per-row state
+      float thr = row_ok ? -INFINITY : INFINITY;     // TOPK: append threshold
+      int cnt = 0;                                   // TOPK: candidates buffered
+      unsigned long long* rowbuf = nullptr;
+      float ts = 0.f; int32_t ti = -1; unsigned long long ccount = 0;
+      if (MODE == MODE_TOPK) rowbuf = P.part_keys + ((size_t)item * BM + row_in_tile) * P.cap;
+      if (MODE == MODE_COUNT && row_ok) { ts = P.thr_score[row]; ti = P.thr_index[row]; }
+
+      for (int64_t t = t0; t < t1; ++t) {
+        mbar_wait(smem_u32(&tail->tmem_full[as]), aphase);
+        tc_fence_after();
+        const int64_t col0 = t * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
+          tmem_ld_wait();
+          const int64_t cbase = col0 + c * 32;
+          const int64_t rem = P.n_posts - cbase;
+          const int nvalid = rem >= 32 ? 32 : (rem > 0 ? (int)rem : 0);
+          if (nvalid == 0) continue;                 // warp-uniform
+
+          if (MODE == MODE_TOPK) {
+            const uint32_t gbase = (uint32_t)(P.index_base + cbase);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float s = __uint_as_float(v[i]);
+              if (i < nvalid && s >= thr) {
+                rowbuf[cnt] = make_key(s, gbase + i);
+                ++cnt;
+              }
+            }
+            if (P.labels != nullptr) {
+              // S[label[j], j]: lane i holds the label of column cbase+i; the owner row is a lane of
+              // this warp iff label - (m_tile*128 + q*32) is in [0, 32)
+              int tgt = -1;
+              if (lane < nvalid) tgt = P.labels[cbase + lane] - (m_tile * BM + q * 32);
+              const uint32_t hit = __ballot_sync(0xffffffffu, tgt >= 0 && tgt < 32);
+              if (hit) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  if ((hit >> i) & 1u) {
+                    const int owner = __shfl_sync(0xffffffffu, tgt, i);
+                    if (lane == owner) P.pos_score[cbase + i] = __uint_as_float(v[i]);
+                  }
+                }
+              }
+            }
+            // keep room for the next 32-column chunk
+            uint32_t full = __ballot_sync(0xffffffffu, cnt > P.cap - 32);
+            if (full) {
+              __syncwarp();
+              while (full) {
+                const int l = __ffs(full) - 1;
+                full &= full - 1;
+                const int n = __shfl_sync(0xffffffffu, cnt, l);
+                unsigned long long* b = P.part_keys + ((size_t)item * BM + q * 32 + l) * P.cap;
+                float nthr;
+                const int kept = warp_select(b, n, P.k, P.keep_limit, false, hist, &nthr);
+                if (lane == l) { cnt = kept; thr = fmaxf(thr, nthr); }
+              }
+              __syncwarp();
+            }
+          } else if (MODE == MODE_DENSE) {
+            if (row_ok) {
+              float* dst = P.dense + (int64_t)row * P.ld_dense + cbase;
+              if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                  *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                                                     __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < nvalid) dst[i] = __uint_as_float(v[i]);
+              }
+            }
+          } else {   // MODE_COUNT
+            if (ti >= 0) {
+              const int64_t gbase = P.index_base + cbase;
+              int local = 0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float s = __uint_as_float(v[i]);
+                const bool before = (s > ts) || (s == ts && (gbase + i) < (int64_t)ti);
+                local += (i < nvalid && before) ? 1 : 0;
+              }
+              ccount += (unsigned long long)local;
+            }
+          }
+        }
+        // release this accumulator stage to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tail->tmem_empty[as]));
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+
+      // ---- end of item ----
+      if (MODE == MODE_TOPK) {
+        uint32_t over = __ballot_sync(0xffffffffu, cnt > P.k);
+        __syncwarp();
+        while (over) {
+          const int l = __ffs(over) - 1;
+          over &= over - 1;
+          const int n = __shfl_sync(0xffffffffu, cnt, l);
+          unsigned long long* b = P.part_keys + ((size_t)item * BM + q * 32 + l) * P.cap;
+          float nthr;
+          const int kept = warp_select(b, n, P.k, P.k, true, hist, &nthr);
+          if (lane == l) cnt = kept;
+        }
+        P.part_cnt[(size_t)item * BM + row_in_tile] = cnt;
+      } else if (MODE == MODE_COUNT) {
+        if (row_ok && ti >= 0 && ccount) atomicAdd(P.count_out + row, ccount);
+      }
+    }
+  }
+
+  // =========================== teardown ===========================
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block-wide bitonic sort (descending) of n_pow2 u64 keys in shared memory.
+// ---------------------------------------------------------------------------------------------
+__device__ void block_bitonic_desc(unsigned long long* keys, int n_pow2) {
+  for (int size = 2; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        unsigned long long a = keys[lo], b = keys[hi];
+        if ((a < b) == desc) { keys[lo] = b; keys[hi] = a; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// One block per brand: gather the per-split candidate lists of this row, sort, emit the top-k.
+__global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long long* __restrict__ part_keys,
+                                                             const int* __restrict__ part_cnt, int num_m_tiles,
+                                                             int splits, int cap, int k, float* __restrict__ out_s,
+                                                             int32_t* __restrict__ out_i) {
+  extern __shared__ unsigned long long skeys[];
+  __shared__ int offs[1025];
+  const int b = blockIdx.x, m_tile = b / BM, r = b % BM;
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int s = 0; s < splits; ++s) {
+      offs[s] = acc;
+      acc += part_cnt[((size_t)s * num_m_tiles + m_tile) * BM + r];
+    }
+    offs[splits] = acc;
+  }
+  __syncthreads();
+  const int total = offs[splits];
+  const int np2 = next_pow2(total > 1 ? total : 2);
+  for (int s = 0; s < splits; ++s) {
+    const int n = offs[s + 1] - offs[s];
+    const unsigned long long* src = part_keys + (((size_t)s * num_m_tiles + m_tile) * BM + r) * cap;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) skeys[offs[s] + i] = src[i];
+  }
+  for (int i = total + threadIdx.x; i < np2; i += blockDim.x) skeys[i] = 0ull;
+  block_bitonic_desc(skeys, np2);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    if (i < total) {
+      out_s[(size_t)b * k + i] = key_score(skeys[i]);
+      out_i[(size_t)b * k + i] = (int32_t)key_index(skeys[i]);
+    } else {
+      out_s[(size_t)b * k + i] = -INFINITY;
+      out_i[(size_t)b * k + i] = -1;
+    }
+  }
+}
+
+// Merge g lists [g, nb, k_in] of (score, index) into [nb, k_out] (multi-GPU exchange step).
+__global__ void __launch_bounds__(256) merge_lists_kernel(const float* __restrict__ in_s, const int32_t* __restrict__ in_i,
+                                                          int g, int nb, int k_in, float* __restrict__ out_s,
+                                                          int32_t* __restrict__ out_i, int k_out) {
+  extern __shared__ unsigned long long skeys[];
+  const int b = blockIdx.x;
+  const int total = g * k_in;
+  const int np2 = next_pow2(total > 1 ? total : 2);
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+    unsigned long long key = 0ull;
+    if (i < total) {
+      const int gi = i / k_in, ki = i % k_in;
+      const size_t src = ((size_t)gi * nb + b) * k_in + ki;
+      const int32_t idx = in_i[src];
+      if (idx >= 0) key = make_key(in_s[src], (uint32_t)idx);
+    }
+    skeys[i] = key;
+  }
+  block_bitonic_desc(skeys, np2);
+  for (int i = threadIdx.x; i < k_out; i += blockDim.x) {
+    const unsigned long long key = i < np2 ? skeys[i] : 0ull;
+    if (key != 0ull) {
+      out_s[(size_t)b * k_out + i] = key_score(key);
+      out_i[(size_t)b * k_out + i] = (int32_t)key_index(key);
+    } else {
+      out_s[(size_t)b * k_out + i] = -INFINITY;
+      out_i[(size_t)b * k_out + i] = -1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || p == nullptr) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// [rows, d] bf16 row-major with leading dimension ld -> 2-D tensor map, box = 64 (K) x box_rows,
+// SWIZZLE_128B, out-of-bounds elements (row tails, K tail) read as zero.
+static int make_operand_map(CUtensorMap* map, const void* ptr, int64_t rows, int d, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return FRX_E_DEVICE; }
+  cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return FRX_E_CUDA; }
+  return FRX_OK;
+}
+
+struct Plan {
+  int num_m_tiles, splits, cap, keep_limit, grid;
+  int64_t num_n_tiles;
+  size_t keys_bytes, cnt_bytes;
+};
+
+static Plan make_plan(int nb, int64_t n_posts, int k, int mode) {
+  Plan p{};
+  const int sms = num_sms();
+  p.num_m_tiles = (nb + BM - 1) / BM;
+  p.num_n_tiles = (n_posts + BN - 1) / BN;
+  int64_t smax = p.num_n_tiles;
+  if (mode == MODE_TOPK && smax > MAX_MERGE_KEYS / k) smax = MAX_MERGE_KEYS / k;
+  if (smax > 1024) smax = 1024;
+  if (smax < 1) smax = 1;
+  // pick the split count that fills whole waves of `sms` CTAs; prefer fewer, longer items
+  int best = 1; double best_eff = -1.0;
+  for (int s = 1; s <= (int)smax; ++s) {
+    const long items = (long)p.num_m_tiles * s;
+    const long waves = (items + sms - 1) / sms;
+    double eff = (double)items / (double)(waves * sms);
+    if (waves > 8 && s > 1) break;               // long enough; more splits only add merge work
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+  }
+  p.splits = best;
+  const long items = (long)p.num_m_tiles * p.splits;
+  p.grid = (int)(items < sms ? items : sms);
+  int cap = 1024;
+  while (cap < 4 * k) cap <<= 1;
+  p.cap = cap;
+  p.keep_limit = k + k / 4;
+  p.keys_bytes = (size_t)items * BM * cap * sizeof(unsigned long long);
+  p.cnt_bytes = (((size_t)items * BM * sizeof(int)) + 255) & ~(size_t)255;
+  return p;
+}
+
+template <int MODE>
+static int launch_score(const uint16_t* a, int64_t ld_a, const uint16_t* b, int64_t ld_b, int nb, int64_t n_posts, int d,
+                        const Plan& plan, ScoreParams& P, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  int rc = make_operand_map(&ma, a, nb, d, ld_a, BM);
+  if (rc) return rc;
+  rc = make_operand_map(&mb, b, n_posts, d, ld_b, BN);
+  if (rc) return rc;
+  P.nb = nb;
+  P.n_posts = n_posts;
+  P.num_k_blocks = (d + BK - 1) / BK;
+  P.num_m_tiles = plan.num_m_tiles;
+  P.num_n_tiles = plan.num_n_tiles;
+  P.splits = plan.splits;
+  FRX_CUDA(cudaFuncSetAttribute(score_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  score_kernel<MODE><<<plan.grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
+static int check_operands(const char* fn, const uint16_t* a, int64_t ld_a, const uint16_t* b, int64_t ld_b, int nb,
+                          int64_t n_posts, int d, int64_t index_base) {
+  FRX_CHECK_ARG(a && b, "%s: NULL operand", fn);
+  FRX_CHECK_ARG(nb > 0 && n_posts > 0 && d > 0, "%s: empty problem nb=%d n_posts=%lld d=%d", fn, nb, (long long)n_posts, d);
+  FRX_CHECK_ARG(ld_a >= d && ld_b >= d && ld_a % 8 == 0 && ld_b % 8 == 0, "%s: leading dimensions must be >= d and multiples of 8", fn);
+  FRX_CHECK_ARG(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0, "%s: operands must be 16-byte aligned", fn);
+  FRX_CHECK_ARG(index_base >= 0 && index_base + n_posts <= 2147483647LL, "%s: index_base + n_posts must fit int32", fn);
+  int dev = 0;
+  FRX_CUDA(cudaGetDevice(&dev));
+  return frx_device_check(dev);
+}
+
+}  // namespace frx
+
+extern "C" {
+
+size_t frx_score_topk_workspace_bytes(int nb, int64_t n_posts, int d, int k) {
+  (void)d;
+  if (nb <= 0 || n_posts <= 0 || k <= 0 || k > 1024) return 0;
+  frx::Plan p = frx::make_plan(nb, n_posts, k, frx::MODE_TOPK);
+  return p.keys_bytes + p.cnt_bytes + 256;
+}
+
+int frx_score_topk(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* post_bf16, int64_t ld_b, int nb,
+                   int64_t n_posts, int d, int k, const int32_t* labels, int64_t index_base, float* topk_scores,
+                   int32_t* topk_index, float* pos_score, float* dense_out, int64_t ld_dense, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  using namespace frx;
+  int rc = check_operands("frx_score_topk", brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, index_base);
+  if (rc) return rc;
+  FRX_CHECK_ARG(k >= 1 && k <= 1024, "frx_score_topk: k=%d outside 1..1024", k);
+  FRX_CHECK_ARG(topk_scores && topk_index, "frx_score_topk: NULL output");
+  FRX_CHECK_ARG((labels == nullptr) == (pos_score == nullptr), "frx_score_topk: labels and pos_score go together");
+  FRX_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "frx_score_topk: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan plan = make_plan(nb, n_posts, k, MODE_TOPK);
+  const size_t need = plan.keys_bytes + plan.cnt_bytes + 256;
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("frx_score_topk: workspace %zu bytes, need %zu", workspace_bytes, need);
+    return FRX_E_WORKSPACE;
+  }
+  ScoreParams P{};
+  P.index_base = index_base;
+  P.k = k;
+  P.cap = plan.cap;
+  P.keep_limit = plan.keep_limit;
+  P.part_cnt = reinterpret_cast<int*>(workspace);
+  P.part_keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(workspace) + plan.cnt_bytes);
+  P.labels = labels;
+  P.pos_score = pos_score;
+  if (pos_score) FRX_CUDA(cudaMemsetAsync(pos_score, 0xFF, (size_t)n_posts * sizeof(float), st));   // NaN
+  rc = launch_score<MODE_TOPK>(brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, plan, P, st);
+  if (rc) return rc;
+  const int total_max = plan.splits * k;
+  int np2 = 2;
+  while (np2 < total_max) np2 <<= 1;
+  const size_t msmem = (size_t)np2 * sizeof(unsigned long long);
+  if (msmem > 48 * 1024)
+    FRX_CUDA(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+  merge_partials_kernel<<<nb, 256, msmem, st>>>(P.part_keys, P.part_cnt, plan.num_m_tiles, plan.splits, plan.cap, k,
+                                                topk_scores, topk_index);
+  FRX_LAUNCH_CHECK();
+  if (dense_out) return frx_score_dense(brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, dense_out, ld_dense, stream);
+  return FRX_OK;
+}
+
+int frx_score_dense(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* post_bf16, int64_t ld_b, int nb,
+                    int64_t n_posts, int d, float* dense_out, int64_t ld_dense, void* stream) {
+  using namespace frx;
+  int rc = check_operands("frx_score_dense", brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, 0);
+  if (rc) return rc;
+  FRX_CHECK_ARG(dense_out && ld_dense >= n_posts, "frx_score_dense: bad output");
+  Plan plan = make_plan(nb, n_posts, 1, MODE_DENSE);
+  ScoreParams P{};
+  P.dense = dense_out;
+  P.ld_dense = ld_dense;
+  return launch_score<MODE_DENSE>(brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, plan, P, (cudaStream_t)stream);
+}
+
+int frx_score_count(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* post_bf16, int64_t ld_b, int nb,
+                    int64_t n_posts, int d, int64_t index_base, const float* thr_score, const int32_t* thr_index,
+                    unsigned long long* count_out, void* stream) {
+  using namespace frx;
+  int rc = check_operands("frx_score_count", brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, index_base);
+  if (rc) return rc;
+  FRX_CHECK_ARG(thr_score && thr_index && count_out, "frx_score_count: NULL pointer");
+  Plan plan = make_plan(nb, n_posts, 1, MODE_COUNT);
+  ScoreParams P{};
+  P.index_base = index_base;
+  P.thr_score = thr_score;
+  P.thr_index = thr_index;
+  P.count_out = count_out;
+  return launch_score<MODE_COUNT>(brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, plan, P, (cudaStream_t)stream);
+}
+
+int frx_topk_merge(const float* in_scores, const int32_t* in_index, int g, int nb, int k_in, float* out_scores,
+                   int32_t* out_index, int k_out, void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(in_scores && in_index && out_scores && out_index, "frx_topk_merge: NULL pointer");
+  FRX_CHECK_ARG(g >= 1 && nb >= 1 && k_in >= 1 && k_out >= 1, "frx_topk_merge: bad sizes");
+  FRX_CHECK_ARG((long)g * k_in <= MAX_MERGE_KEYS, "frx_topk_merge: g*k_in = %ld exceeds %d", (long)g * k_in, MAX_MERGE_KEYS);
+  int np2 = 2;
+  while (np2 < g * k_in) np2 <<= 1;
+  const size_t msmem = (size_t)np2 * sizeof(unsigned long long);
+  if (msmem > 48 * 1024)
+    FRX_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+  merge_lists_kernel<<<nb, 256, msmem, (cudaStream_t)stream>>>(in_scores, in_index, g, nb, k_in, out_scores, out_index, k_out);
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,282 @@
+"""torch.Tensor-level wrappers over the C ABI (include/frx.h).
+
+torch is plumbing here: it owns device memory and the current stream; every wrapper unwraps
+``data_ptr()`` and calls the hand-written sm_100a kernels in libfrx_b200.so.  Inputs that are not
+CUDA tensors are rejected -- there is no CPU path.
+"""
+import torch
+
+from . import _lib
+
+VISUAL_NORM, TEXT_NORM, FINAL_NORM = 1, 2, 4
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _req(t, dtype, name, dims=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.FrxError("%s must be a CUDA tensor (fancyrec_b200 has no CPU fallback)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    if dims is not None and t.dim() != dims:
+        raise ValueError("%s must be %d-D" % (name, dims))
+    return t
+
+
+def round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+# ---------------------------------------------------------------------------------------------
+def finalize_posts(visual, text=None, row_ptr=None, row_idx=None, visual_norm=False, text_norm=False,
+                   final_norm=True, want_f32=False, want_bf16=True):
+    """A1-A3 in one pass.  Returns (out_f32 | None, out_bf16 | None); out_bf16 is [NP, round_up(D, 64)]
+    with zero padding, the operand layout of score_*."""
+    lib = _lib.load()
+    _req(visual, torch.float32, "visual", 2)
+    dv = visual.shape[1]
+    if row_ptr is not None:
+        _req(row_ptr, torch.int64, "row_ptr", 1)
+        n_posts = row_ptr.numel() - 1
+    else:
+        n_posts = visual.shape[0]
+    if row_idx is not None:
+        _req(row_idx, torch.int32, "row_idx", 1)
+    dt = 0
+    if text is not None:
+        _req(text, torch.float32, "text", 2)
+        dt = text.shape[1]
+        if text.shape[0] != n_posts:
+            raise ValueError("text has %d rows, expected %d" % (text.shape[0], n_posts))
+    d = dv + dt
+    flags = (VISUAL_NORM if visual_norm else 0) | (TEXT_NORM if text_norm else 0) | (FINAL_NORM if final_norm else 0)
+    out_f32 = torch.empty((n_posts, d), dtype=torch.float32, device=visual.device) if want_f32 else None
+    ld = round_up(d, 64)
+    out_bf16 = torch.empty((n_posts, ld), dtype=torch.bfloat16, device=visual.device) if want_bf16 else None
+    with torch.cuda.device(visual.device):
+        rc = lib.frx_finalize_posts(_ptr(visual), _ptr(row_ptr), _ptr(row_idx), _ptr(text), n_posts, dv, dt, flags,
+                                    _ptr(out_f32), _ptr(out_bf16), ld, _stream(visual))
+    _lib.check(rc, "frx_finalize_posts")
+    return out_f32, out_bf16
+
+
+def brand_embed(w, e, brand_ids=None, nb=None):
+    """A4: out[i] = mean_a W[ids[i], a] * E[a, :]  -> [nb, D] fp32."""
+    lib = _lib.load()
+    _req(w, torch.float32, "w", 2)
+    _req(e, torch.float32, "e", 2)
+    if brand_ids is not None:
+        _req(brand_ids, torch.int64, "brand_ids", 1)
+        nb = brand_ids.numel()
+    elif nb is None:
+        nb = w.shape[0]
+    a, d = e.shape
+    if w.shape[1] != a:
+        raise ValueError("w is [*, %d] but e is [%d, *]" % (w.shape[1], a))
+    out = torch.empty((nb, d), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        rc = lib.frx_brand_embed(_ptr(w), w.shape[0], _ptr(e), _ptr(brand_ids), nb, a, d, _ptr(out), _stream(w))
+    _lib.check(rc, "frx_brand_embed")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+def _operands(brand_bf16, post_bf16, d):
+    _req(brand_bf16, torch.bfloat16, "brand_bf16", 2)
+    _req(post_bf16, torch.bfloat16, "post_bf16", 2)
+    if d is None:
+        d = min(brand_bf16.shape[1], post_bf16.shape[1])
+    return d
+
+
+def score_topk(brand_bf16, post_bf16, k, d=None, labels=None, index_base=0, workspace=None, dense=False):
+    """A5+A6 fused.  Returns dict(scores [NB,k] f32, index [NB,k] i32, pos_score [NP] f32 | None,
+    dense [NB,NP] f32 | None)."""
+    lib = _lib.load()
+    d = _operands(brand_bf16, post_bf16, d)
+    nb, n_posts = brand_bf16.shape[0], post_bf16.shape[0]
+    dev = post_bf16.device
+    need = lib.frx_score_topk_workspace_bytes(nb, n_posts, d, k)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    scores = torch.empty((nb, k), dtype=torch.float32, device=dev)
+    index = torch.empty((nb, k), dtype=torch.int32, device=dev)
+    pos_score = None
+    if labels is not None:
+        _req(labels, torch.int32, "labels", 1)
+        pos_score = torch.empty(n_posts, dtype=torch.float32, device=dev)
+    dense_out = torch.empty((nb, n_posts), dtype=torch.float32, device=dev) if dense else None
+    with torch.cuda.device(dev):
+        rc = lib.frx_score_topk(_ptr(brand_bf16), brand_bf16.stride(0), _ptr(post_bf16), post_bf16.stride(0), nb,
+                                n_posts, d, k, _ptr(labels), index_base, _ptr(scores), _ptr(index), _ptr(pos_score),
+                                _ptr(dense_out), n_posts, _ptr(workspace), workspace.numel(), _stream(post_bf16))
+    _lib.check(rc, "frx_score_topk")
+    return dict(scores=scores, index=index, pos_score=pos_score, dense=dense_out, workspace=workspace)
+
+
+def score_dense(brand_bf16, post_bf16, d=None, out=None):
+    lib = _lib.load()
+    d = _operands(brand_bf16, post_bf16, d)
+    nb, n_posts = brand_bf16.shape[0], post_bf16.shape[0]
+    if out is None:
+        out = torch.empty((nb, n_posts), dtype=torch.float32, device=post_bf16.device)
+    with torch.cuda.device(post_bf16.device):
+        rc = lib.frx_score_dense(_ptr(brand_bf16), brand_bf16.stride(0), _ptr(post_bf16), post_bf16.stride(0), nb,
+                                 n_posts, d, _ptr(out), out.stride(0), _stream(post_bf16))
+    _lib.check(rc, "frx_score_dense")
+    return out
+
+
+def score_count(brand_bf16, post_bf16, thr_score, thr_index, d=None, index_base=0, out=None):
+    """Per brand: number of posts preceding (thr_score, thr_index).  Accumulates into ``out`` (int64)."""
+    lib = _lib.load()
+    d = _operands(brand_bf16, post_bf16, d)
+    nb, n_posts = brand_bf16.shape[0], post_bf16.shape[0]
+    _req(thr_score, torch.float32, "thr_score", 1)
+    _req(thr_index, torch.int32, "thr_index", 1)
+    if out is None:
+        out = torch.zeros(nb, dtype=torch.int64, device=post_bf16.device)
+    with torch.cuda.device(post_bf16.device):
+        rc = lib.frx_score_count(_ptr(brand_bf16), brand_bf16.stride(0), _ptr(post_bf16), post_bf16.stride(0), nb,
+                                 n_posts, d, index_base, _ptr(thr_score), _ptr(thr_index), _ptr(out),
+                                 _stream(post_bf16))
+    _lib.check(rc, "frx_score_count")
+    return out
+
+
+def topk_merge(scores, index, k_out):
+    """[G, NB, k_in] candidate lists -> merged [NB, k_out] (score desc, index asc)."""
+    lib = _lib.load()
+    _req(scores, torch.float32, "scores", 3)
+    _req(index, torch.int32, "index", 3)
+    g, nb, k_in = scores.shape
+    out_s = torch.empty((nb, k_out), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((nb, k_out), dtype=torch.int32, device=scores.device)
+    with torch.cuda.device(scores.device):
+        rc = lib.frx_topk_merge(_ptr(scores), _ptr(index), g, nb, k_in, _ptr(out_s), _ptr(out_i), k_out,
+                                _stream(scores))
+    _lib.check(rc, "frx_topk_merge")
+    return out_s, out_i
+
+
+# ---------------------------------------------------------------------------------------------
+def label_stats(labels, pos_score, nb, index_base=0):
+    lib = _lib.load()
+    _req(labels, torch.int32, "labels", 1)
+    _req(pos_score, torch.float32, "pos_score", 1)
+    dev = labels.device
+    n_pos = torch.empty(nb, dtype=torch.int32, device=dev)
+    best_score = torch.empty(nb, dtype=torch.float32, device=dev)
+    best_index = torch.empty(nb, dtype=torch.int32, device=dev)
+    ws = torch.empty(nb, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.frx_label_stats(_ptr(labels), _ptr(pos_score), labels.numel(), nb, index_base, _ptr(n_pos),
+                                 _ptr(best_score), _ptr(best_index), _ptr(ws), _stream(labels))
+    _lib.check(rc, "frx_label_stats")
+    return n_pos, best_score, best_index
+
+
+def rank_from_topk(topk_index, labels, index_base=0):
+    lib = _lib.load()
+    _req(topk_index, torch.int32, "topk_index", 2)
+    _req(labels, torch.int32, "labels", 1)
+    nb, k = topk_index.shape
+    dev = labels.device
+    hit_mask = torch.empty(nb, dtype=torch.int64, device=dev)
+    first_rank = torch.empty(nb, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.frx_rank_from_topk(_ptr(topk_index), nb, k, _ptr(labels), labels.numel(), index_base,
+                                    _ptr(hit_mask), _ptr(first_rank), _stream(labels))
+    _lib.check(rc, "frx_rank_from_topk")
+    return hit_mask, first_rank
+
+
+def group_positives(labels, pos_score, n_pos):
+    lib = _lib.load()
+    _req(labels, torch.int32, "labels", 1)
+    _req(pos_score, torch.float32, "pos_score", 1)
+    _req(n_pos, torch.int32, "n_pos", 1)
+    nb = n_pos.numel()
+    dev = labels.device
+    seg_ptr = torch.empty(nb + 1, dtype=torch.int64, device=dev)
+    pos_sorted = torch.empty(max(labels.numel(), 1), dtype=torch.float32, device=dev)
+    ws = torch.empty(nb, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.frx_group_positives(_ptr(labels), _ptr(pos_score), labels.numel(), nb, _ptr(n_pos), _ptr(seg_ptr),
+                                     _ptr(pos_sorted), _ptr(ws), _stream(labels))
+    _lib.check(rc, "frx_group_positives")
+    return seg_ptr, pos_sorted
+
+
+def auc_rows(scores, row0, labels, seg_ptr, pos_sorted, best_score, best_index, auc_num, before_first, index_base=0):
+    lib = _lib.load()
+    _req(scores, torch.float32, "scores", 2)
+    _req(auc_num, torch.int64, "auc_num", 1)
+    _req(before_first, torch.int64, "before_first", 1)
+    n_rows, n_posts = scores.shape
+    with torch.cuda.device(scores.device):
+        rc = lib.frx_auc_rows(_ptr(scores), scores.stride(0), row0, n_rows, n_posts, _ptr(labels), _ptr(seg_ptr),
+                              _ptr(pos_sorted), _ptr(best_score), _ptr(best_index), index_base, _ptr(auc_num),
+                              _ptr(before_first), _stream(scores))
+    _lib.check(rc, "frx_auc_rows")
+
+
+# ---------------------------------------------------------------------------------------------
+def triplet_fwd_bwd(brand_ids, brand, post, margin, mean_style, want_grad=True):
+    lib = _lib.load()
+    _req(brand_ids, torch.int64, "brand_ids", 1)
+    _req(brand, torch.float32, "brand", 2)
+    _req(post, torch.float32, "post", 2)
+    b, d = brand.shape
+    dev = brand.device
+    ws = torch.empty(lib.frx_triplet_workspace_bytes(b, d), dtype=torch.uint8, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    d_brand = torch.empty_like(brand) if want_grad else None
+    d_post = torch.empty_like(post) if want_grad else None
+    with torch.cuda.device(dev):
+        rc = lib.frx_triplet_fwd_bwd(_ptr(brand_ids), _ptr(brand), _ptr(post), b, d, float(margin), int(mean_style),
+                                     _ptr(loss), _ptr(d_brand), _ptr(d_post), _ptr(ws), ws.numel(), _stream(brand))
+    _lib.check(rc, "frx_triplet_fwd_bwd")
+    return loss, d_brand, d_post
+
+
+def normalize_rows(x):
+    lib = _lib.load()
+    _req(x, torch.float32, "x", 2)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = lib.frx_normalize_rows(_ptr(x), x.shape[0], x.shape[1], _ptr(out), _stream(x))
+    _lib.check(rc, "frx_normalize_rows")
+    return out
+
+
+def contrastive_fwd_bwd(brand, post, keys, mask_col0, no_intra, temperature, negative_weight, mean_style,
+                        want_grad=True):
+    lib = _lib.load()
+    _req(brand, torch.float32, "brand", 2)
+    _req(post, torch.float32, "post", 2)
+    b, d = brand.shape
+    n_keys = 0
+    if keys is not None:
+        _req(keys, torch.float32, "keys", 2)
+        n_keys = keys.shape[0]
+    dev = brand.device
+    ws = torch.empty(lib.frx_contrastive_workspace_bytes(b, d, n_keys), dtype=torch.uint8, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    d_brand = torch.empty_like(brand) if want_grad else None
+    d_post = torch.empty_like(post) if want_grad else None
+    with torch.cuda.device(dev):
+        rc = lib.frx_contrastive_fwd_bwd(_ptr(brand), _ptr(post), b, d, _ptr(keys), n_keys, int(mask_col0),
+                                         int(bool(no_intra)), float(temperature), float(negative_weight),
+                                         int(mean_style), _ptr(loss), _ptr(d_brand), _ptr(d_post), _ptr(ws),
+                                         ws.numel(), _stream(brand))
+    _lib.check(rc, "frx_contrastive_fwd_bwd")
+    return loss, d_brand, d_post

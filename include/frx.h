@@ -1,0 +1,200 @@
+/*
+ * frx.h -- C ABI of the B200-native brand x post scoring + ranking library
+ *          (libfrx_b200.so, sm_100a only).
+ *
+ * The reference (pinskyrobin/FancyRec) is pure Python/PyTorch and has no FFI of its
+ * own; its callers bind by Python name.  This header is therefore the
+ * boundary a maintainer binds with ctypes from the reference's own modules
+ * (INTEGRATION.md shows the stubs).  Every entry point names the reference lines it
+ * replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer unless the
+ *     parameter name starts with "host_";
+ *   - caller owns every buffer; the library never allocates (query
+ *     frx_*_workspace_bytes and pass the scratch in);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and
+ *     re-entrant across streams as long as buffers/workspaces are distinct;
+ *   - return 0 on success, a negative FRX_E_* code otherwise; frx_last_error()
+ *     returns a thread-local message for the last failing call;
+ *   - there is NO CPU fallback: with no sm_100 device every compute call fails with
+ *     FRX_E_DEVICE.
+ *   - ordering everywhere: (score descending, post index ascending) -- the order
+ *     Python's stable sorted(..., reverse=True) gives at evaluator.py:109.
+ */
+#ifndef FRX_H_
+#define FRX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRX_ABI_VERSION 1
+
+#define FRX_OK          0
+#define FRX_E_ARG      -1   /* bad argument (null pointer, size, alignment)   */
+#define FRX_E_DEVICE   -2   /* no sm_100 device / driver entry point missing  */
+#define FRX_E_WORKSPACE -3  /* workspace too small                            */
+#define FRX_E_CUDA     -4   /* a CUDA runtime/driver call failed              */
+#define FRX_E_UNSUPPORTED -5
+
+/* flags of frx_finalize_posts */
+#define FRX_VISUAL_NORM 1   /* model.py:207-208  */
+#define FRX_TEXT_NORM   2   /* model.py:301-302, :382-383 */
+#define FRX_FINAL_NORM  4   /* evaluator.py:27-28 (cal_sim's l2norm of the post operand) */
+
+int         frx_abi_version(void);
+const char* frx_last_error(void);
+/* 0 when device `ordinal` is an sm_100 part this library can run on, else FRX_E_DEVICE. */
+int         frx_device_check(int ordinal);
+
+/* ---------------------------------------------------------------------------------------------
+ * A1-A3  post-embedding finalisation, one HBM pass.
+ * Replaces: torch.mean(frames, 0) in util/data_provider.py:40,91,132 (mean over ALL frames of a
+ * post, rows taken from the feature.bin matrix of util/imgbigfile.py:7-16), model.l2norm
+ * (model.py:39-44) per branch, torch.cat((visual, text), 1) (model.py:482-485) and the row l2norm
+ * of evaluator.py:14-19,27-28.
+ *
+ *   visual   [n_rows, dv] fp32 row-major.  With row_ptr == NULL it is one row per post.
+ *   row_ptr  [n_posts + 1] int64 CSR offsets: post p owns frame rows row_ptr[p] .. row_ptr[p+1]-1
+ *            (or entries of row_idx in that range), mean-pooled.  NULL = no pooling.
+ *   row_idx  optional [row_ptr[n_posts]] int32 gather list into `visual` rows (frames of one video
+ *            are not guaranteed contiguous, preprocess/get_frameInfo.py:55).  NULL = contiguous.
+ *   text     [n_posts, dt] fp32 or NULL (dt = 0).
+ *   out_f32  [n_posts, dv + dt] fp32 or NULL.
+ *   out_bf16 [n_posts, ld_bf16] bf16 bits or NULL; columns dv+dt .. ld_bf16-1 are zero-filled
+ *            (operand layout of frx_score_*: ld_bf16 % 8 == 0).
+ * A zero row yields NaN exactly like the reference (no epsilon).
+ */
+int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_t* row_idx,
+                       const float* text, int64_t n_posts, int dv, int dt, int flags,
+                       float* out_f32, uint16_t* out_bf16, int64_t ld_bf16, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * A4  brand embedding without the [NB, A, D] intermediate.
+ * Replaces: BrandAspects.forward in eval mode (model.py:419-428; dropout off, L1Penalty forward =
+ * identity) followed by .permute(1,0,2).mean(0) (model.py:594, evaluator.py:93-94):
+ *      out[i, :] = (1/A) * sum_a W[ids[i], a] * E[a, :]
+ *   w [w_rows, a] fp32 (nn.Embedding table, brand_num + 1 rows), e [a, d] fp32,
+ *   brand_ids [nb] int64 or NULL (= 0 .. nb-1), out_f32 [nb, d].
+ */
+int frx_brand_embed(const float* w, int64_t w_rows, const float* e, const int64_t* brand_ids,
+                    int nb, int a, int d, float* out_f32, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * A5 + A6  cosine-score contraction with the per-brand top-k fused into the GEMM epilogue.
+ * Replaces: cal_sim's im.mm(s.t()) (evaluator.py:29), the device->host copy of the whole score
+ * matrix (evaluator.py:96) and the per-brand sorted() / np.argsort (evaluator.py:108-109,124).
+ * tcgen05.mma (bf16 in, fp32 accumulate in TMEM), TMA operand loads; the score matrix is never
+ * written unless `dense_out` is given.
+ *
+ *   brand_bf16 [nb, ld_a], post_bf16 [n_posts, ld_b]: bf16 bits, rows already L2-normalised,
+ *            ld_* % 8 == 0, columns d .. ld-1 zero, base pointers 16-byte aligned.
+ *   k        1 .. 1024 (lists are padded with score = -inf, index = -1 when n_posts < k).
+ *   labels   optional [n_posts] int32 brand label of each post; when given, pos_score[j] receives
+ *            the score of post j against its own brand, S[labels[j], j] (0 <= labels[j] < nb), the
+ *            only entries the "positive" side of AUC / first-positive-rank needs.  Posts whose
+ *            label is outside [0, nb) get NaN.
+ *   index_base  global index of post 0 of this shard; output indices are index_base + local and
+ *            must fit int32.
+ *   topk_scores [nb, k] fp32, topk_index [nb, k] int32, sorted by (score desc, index asc).
+ *   dense_out optional [nb, ld_dense] fp32: the full score tile (debug / AUC path), same
+ *            accumulators as the fused path, bit for bit.
+ */
+size_t frx_score_topk_workspace_bytes(int nb, int64_t n_posts, int d, int k);
+int frx_score_topk(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* post_bf16, int64_t ld_b,
+                   int nb, int64_t n_posts, int d, int k,
+                   const int32_t* labels, int64_t index_base,
+                   float* topk_scores, int32_t* topk_index, float* pos_score,
+                   float* dense_out, int64_t ld_dense,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Dense score tile only (no top-k): out[b, j] = brand_b . post_j, for the score-tolerance tests and
+ * the AUC row sweep.  Same kernel mainloop as frx_score_topk. */
+int frx_score_dense(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* post_bf16, int64_t ld_b,
+                    int nb, int64_t n_posts, int d, float* dense_out, int64_t ld_dense, void* stream);
+
+/* Count pass: for every brand b, the number of posts that precede (thr_score[b], thr_index[b]) in
+ * the stated order: #{ j : S[b,j] > thr_score[b]  or  (S[b,j] == thr_score[b] and index_base + j <
+ * thr_index[b]) }.  With the threshold set to a brand's best positive this IS rank_of_first_pos
+ * (evaluator.py:116) without materialising S.  count_out [nb] int64 is ACCUMULATED into (caller
+ * zeroes it; shards add up).  Rows with thr_index[b] < 0 are skipped. */
+int frx_score_count(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* post_bf16, int64_t ld_b,
+                    int nb, int64_t n_posts, int d, int64_t index_base,
+                    const float* thr_score, const int32_t* thr_index,
+                    unsigned long long* count_out, void* stream);
+
+/* Merge G candidate lists per brand (the multi-GPU exchange step after the all-gather):
+ * in_scores / in_index [g, nb, k_in] -> out [nb, k_out], same order; entries with index < 0 are
+ * padding.  Requires g * k_in <= 16384. */
+int frx_topk_merge(const float* in_scores, const int32_t* in_index, int g, int nb, int k_in,
+                   float* out_scores, int32_t* out_index, int k_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * A6-A9  rank statistics (integers; the float64 metric values are functions of these).
+ *
+ * frx_label_stats: n_pos[b] = #{j : labels[j] == b}; best_score/best_index[b] = the best positive
+ * of brand b under the stated order (index = index_base + j; -1 when n_pos[b] == 0).
+ * Replaces the pos/neg split of evaluator.py:111-112 and the argmax side of :116.
+ */
+int frx_label_stats(const int32_t* labels, const float* pos_score, int64_t n_posts, int nb,
+                    int64_t index_base, int32_t* n_pos, float* best_score, int32_t* best_index,
+                    void* workspace_nb_u64, void* stream);
+
+/* frx_rank_from_topk: one warp per brand walks its sorted top-k list.
+ *   hit_mask[b]  bit r (r < 64) set when the post at rank r is labelled b -- the relevance vector
+ *                ndcg_at_k reads (evaluator.py:119-120, util/ndcg.py:37);
+ *   first_rank[b] rank of the first positive inside the list, or -1 when the list holds none
+ *                (then frx_score_count supplies it).
+ * labels are indexed with (topk_index - index_base); entries outside [0, n_posts) count as misses. */
+int frx_rank_from_topk(const int32_t* topk_index, int nb, int k, const int32_t* labels, int64_t n_posts,
+                       int64_t index_base, unsigned long long* hit_mask, int32_t* first_rank, void* stream);
+
+/* frx_auc_rows: exact AUC numerators from dense score rows (evaluator.py:111-113):
+ *   auc_num[row0 + r] += sum over positives e of brand (row0+r) of #{negatives el : e > el}
+ *   before_first[row0 + r] += #{j : (S[r,j], j) precedes the brand's best positive}
+ * scores [n_rows, ld] fp32 is the dense tile of brands row0 .. row0+n_rows-1 (frx_score_dense);
+ * pos_sorted holds every brand's positive scores grouped by brand in ascending order, seg_ptr [nb+1]
+ * the group offsets (frx_group_positives builds both).  Outputs are accumulated (caller zeroes). */
+int frx_group_positives(const int32_t* labels, const float* pos_score, int64_t n_posts, int nb,
+                        const int32_t* n_pos, int64_t* seg_ptr, float* pos_sorted,
+                        void* workspace_nb_i64, void* stream);
+int frx_auc_rows(const float* scores, int64_t ld, int row0, int n_rows, int64_t n_posts,
+                 const int32_t* labels, const int64_t* seg_ptr, const float* pos_sorted,
+                 const float* best_score, const int32_t* best_index, int64_t index_base,
+                 unsigned long long* auc_num, unsigned long long* before_first, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * A12  TripletLoss on the in-batch similarity tile (loss.py:87-143), forward + backward fused.
+ *   S[i,j] = post_i . brand_j (fp32); rank weights (loss.py:96-105); hinge with same-brand mask
+ *   (loss.py:107-129); weights broadcast along the column index (loss.py:131-132); sum | mean.
+ *   Outputs: loss[1] fp32, d_brand [b, d], d_post [b, d] (gradients of the loss itself; scale by the
+ *   upstream gradient on the host side).  mean_style: 0 = 'sum', 1 = 'mean'.
+ */
+size_t frx_triplet_workspace_bytes(int b, int d);
+int frx_triplet_fwd_bwd(const int64_t* brand_ids, const float* brand, const float* post, int b, int d,
+                        float margin, int mean_style, float* loss, float* d_brand, float* d_post,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* A13  ContrastiveLoss (loss_ctrs.py:179-214), forward + backward.
+ *   keys [n_keys, d]: the queue AFTER enqueue (loss_ctrs.py:138-147) or NULL for the
+ *   no_queue / no_intra variants (keys = normalised posts); mask_col0 = column masked for row 0
+ *   (queue pointer after the move, loss_ctrs.py:149-159; row i masks column mask_col0 + i).
+ *   post_norm_out [b, d] receives F.normalize(post) (what the caller enqueues).
+ */
+size_t frx_contrastive_workspace_bytes(int b, int d, int n_keys);
+int frx_contrastive_fwd_bwd(const float* brand, const float* post, int b, int d,
+                            const float* keys, int n_keys, int mask_col0, int no_intra,
+                            float temperature, float negative_weight, int mean_style,
+                            float* loss, float* d_brand, float* d_post,
+                            void* workspace, size_t workspace_bytes, void* stream);
+/* F.normalize(post) rows (eps 1e-12), what ContrastiveLoss enqueues (loss_ctrs.py:195,200). */
+int frx_normalize_rows(const float* x, int rows, int d, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRX_H_ */

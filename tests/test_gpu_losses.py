@@ -1,0 +1,142 @@
+"""GPU parity: TripletLoss / ContrastiveLoss forward + backward against the reference's autograd
+(tests/golden/losses.npz) and the fp64 oracle.  fp32 kernels: rtol 2e-4 on loss, 2e-3 on gradients
+(sum over B^2 hinge terms / softmax over B + Q logits, different summation order)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import losses as oloss
+from oracle import synth
+from tests.gpu_util import dev, to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("style", ["sum", "mean"])
+def test_triplet_golden(golden_dir, style):
+    from fancyrec_b200 import loss as floss
+    g = np.load(os.path.join(golden_dir, "losses.npz"))
+    ids, brand, post = synth.loss_inputs()
+    for mv in (False, True):
+        bt = to_dev(brand).requires_grad_()
+        pt = to_dev(post).requires_grad_()
+        crit = floss.TripletLoss(margin=0.2, max_violation=mv, cost_style=style)
+        val = crit(torch.from_numpy(ids), bt, pt)
+        (val * 1.0).backward()
+        key = "triplet_%s_mv%d" % (style, int(mv))
+        np.testing.assert_allclose(val.item(), g[key + "_loss"], rtol=2e-5)
+        np.testing.assert_allclose(bt.grad.cpu().numpy(), g[key + "_dbrand"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(pt.grad.cpu().numpy(), g[key + "_dpost"], rtol=1e-4, atol=1e-6)
+    for direction in ("p2b", "b2p"):
+        with pytest.raises(TypeError):
+            floss.TripletLoss(margin=0.2, direction=direction)(torch.from_numpy(ids), to_dev(brand), to_dev(post))
+
+
+@pytest.mark.parametrize("b,d", [(512, 1024), (100, 96), (257, 300)])
+def test_triplet_vs_oracle_config3(b, d):
+    from fancyrec_b200 import ops
+    rs = np.random.RandomState(b + d)
+    ids = rs.randint(0, 51, b).astype(np.int64)
+    brand = (rs.standard_normal((b, d)) * 0.05).astype(np.float32)
+    post = (rs.standard_normal((b, d)) * 0.05).astype(np.float32) + brand * 0.5
+    for style in (0, 1):
+        loss, db, dp = ops.triplet_fwd_bwd(to_dev(ids), to_dev(brand), to_dev(post), 0.2, style)
+        wl, wdb, wdp, aux = oloss.triplet_loss(ids, brand, post, 0.2, 'mean' if style else 'sum')
+        np.testing.assert_allclose(loss.item(), wl, rtol=2e-4)
+        scale = np.abs(wdb).max()
+        np.testing.assert_allclose(db.cpu().numpy(), wdb, rtol=2e-3, atol=2e-3 * scale)
+        np.testing.assert_allclose(dp.cpu().numpy(), wdp, rtol=2e-3, atol=2e-3 * np.abs(wdp).max())
+
+
+def test_triplet_upstream_gradient_scales():
+    from fancyrec_b200 import loss as floss
+    ids, brand, post = synth.loss_inputs()
+    bt = to_dev(brand).requires_grad_()
+    val = floss.TripletLoss(margin=0.2)(torch.from_numpy(ids), bt, to_dev(post))
+    (val * 3.0).backward()
+    g3 = bt.grad.clone()
+    bt.grad = None
+    floss.TripletLoss(margin=0.2)(torch.from_numpy(ids), bt, to_dev(post)).backward()
+    torch.testing.assert_close(g3, bt.grad * 3.0)
+
+
+@pytest.mark.parametrize("style", ["sum", "mean"])
+@pytest.mark.parametrize("mode", ["queue", "no_queue", "no_intra"])
+def test_contrastive_golden(golden_dir, style, mode):
+    import types
+    from fancyrec_b200 import loss_ctrs as fctrs
+    g = np.load(os.path.join(golden_dir, "losses.npz"))
+    b, d = 24, 32
+    opt = types.SimpleNamespace(cost_style=style, queue_size=2 * b, common_embedding_size=d,
+                                no_queue=(mode == "no_queue"), no_intra=(mode == "no_intra"))
+    crit = fctrs.ContrastiveLoss(opt).to(dev())
+    for step in range(3):
+        _, brand, post = synth.loss_inputs(seed=600 + step)
+        bt = to_dev(brand).requires_grad_()
+        pt = to_dev(post).requires_grad_()
+        val = crit(bt, pt)
+        val.backward()
+        key = "ctr_%s_%s_s%d" % (style, mode, step)
+        np.testing.assert_allclose(val.item(), g[key + "_loss"], rtol=1e-4)
+        np.testing.assert_allclose(bt.grad.cpu().numpy(), g[key + "_dbrand"], rtol=5e-3, atol=5e-5)
+        np.testing.assert_allclose(pt.grad.cpu().numpy(), g[key + "_dpost"], rtol=5e-3, atol=5e-5)
+        np.testing.assert_allclose(crit.queue.cpu().numpy(), g[key + "_queue"], rtol=1e-5, atol=1e-7)
+        assert int(crit.queue_ptr[0]) == int(g[key + "_ptr"][0])
+
+
+def test_contrastive_bad_queue_size_errors_like_reference(golden_dir):
+    import types
+    from fancyrec_b200 import loss_ctrs as fctrs
+    g = np.load(os.path.join(golden_dir, "losses.npz"))
+    want = [str(x) for x in g["ctr_bad_queue_errors"]]
+    _, brand, post = synth.loss_inputs()
+    b, d = brand.shape
+    opt = types.SimpleNamespace(cost_style="sum", queue_size=2 * b + 4, common_embedding_size=d, no_queue=False,
+                                no_intra=False)
+    crit = fctrs.ContrastiveLoss(opt).to(dev())
+    got = []
+    for step in range(3):
+        try:
+            crit(to_dev(brand), to_dev(post))
+            got.append("ok")
+        except (IndexError, RuntimeError) as ex:
+            got.append(type(ex).__name__)
+    assert got == want
+
+
+def test_contrastive_vs_oracle_config3():
+    from fancyrec_b200 import ops
+    rs = np.random.RandomState(5)
+    b, d, q = 512, 1024, 5120
+    brand = rs.standard_normal((b, d)).astype(np.float32)
+    post = (rs.standard_normal((b, d)) + brand).astype(np.float32)
+    queue = rs.standard_normal((q, d)).astype(np.float32)
+    queue /= np.linalg.norm(queue, axis=1, keepdims=True)
+    wl, wdb, wdp, nq, nptr = oloss.contrastive_loss(brand, post, queue=queue, queue_ptr=1024, cost_style='mean')
+    loss, db, dp = ops.contrastive_fwd_bwd(to_dev(brand), to_dev(post), to_dev(nq.astype(np.float32)), nptr, False,
+                                           0.03, 0.8, 1)
+    np.testing.assert_allclose(loss.item(), wl, rtol=2e-4)
+    np.testing.assert_allclose(db.cpu().numpy(), wdb, rtol=5e-3, atol=5e-3 * np.abs(wdb).max())
+    np.testing.assert_allclose(dp.cpu().numpy(), wdp, rtol=5e-3, atol=5e-3 * np.abs(wdp).max())
+
+
+def test_crossclr_lab_golden(golden_dir):
+    from fancyrec_b200 import loss as floss
+    from fancyrec_b200 import loss_ctrs as fctrs
+    g = np.load(os.path.join(golden_dir, "losses.npz"))
+    _, brand, post = synth.loss_inputs()
+    for style in ("sum", "mean"):
+        bt = to_dev(brand).requires_grad_()
+        pt = to_dev(post).requires_grad_()
+        val = fctrs.CrossCLR_onlyIntraModality(cost_style=style).to(dev())(bt, pt)
+        val.backward()
+        np.testing.assert_allclose(val.item(), g["crossclr_%s_loss" % style], rtol=1e-4)
+        np.testing.assert_allclose(bt.grad.cpu().numpy(), g["crossclr_%s_dbrand" % style], rtol=5e-3, atol=5e-5)
+        np.testing.assert_allclose(pt.grad.cpu().numpy(), g["crossclr_%s_dpost" % style], rtol=5e-3, atol=5e-5)
+    bt = to_dev(brand).requires_grad_()
+    val = floss.LabLoss()(bt)
+    val.backward()
+    np.testing.assert_allclose(val.item(), g["lab_loss"], rtol=1e-5)
+    np.testing.assert_allclose(bt.grad.cpu().numpy(), g["lab_dbrand"], rtol=1e-3, atol=1e-6)

@@ -1,0 +1,154 @@
+"""GPU parity: fused score + top-k GEMM, dense tile, count pass, merge -- through the C ABI.
+
+Protocol: (2) scores vs fp32 cal_sim within 1e-3 on the cosine scale (bf16 operands,
+fp32 accumulation); (3) rankings / indices bit-exact against the oracle applied to OUR score tile;
+(4) exact-lattice inputs: bit-exact against the pure fp32 reference scores.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ranking as oref
+from oracle import synth
+from tests.gpu_util import dev, operand, to_dev
+
+pytestmark = pytest.mark.gpu
+
+SCORE_ATOL = 1e-3   # stated tolerance for bf16 inputs (north_star), cosine scale |s| <= 1
+
+
+def _dense_and_topk(brand, posts, k, labels=None, index_base=0):
+    from fancyrec_b200 import ops
+    a, b = operand(brand), operand(posts)
+    d = brand.shape[1]
+    lab = to_dev(labels.astype(np.int32)) if labels is not None else None
+    res = ops.score_topk(a, b, k, d=d, labels=lab, index_base=index_base)
+    dense = ops.score_dense(a, b, d=d)
+    torch.cuda.synchronize()
+    return res, dense.cpu().numpy(), a, b
+
+
+@pytest.mark.parametrize("nb,npost,d,k", [
+    (5, 257, 48, 10), (1, 37, 64, 64), (50, 10000, 1024, 64), (130, 3000, 200, 100),
+    (300, 70001, 256, 100), (64, 5000, 3072, 1000), (129, 513, 72, 1), (1000, 20000, 128, 100),
+])
+def test_topk_matches_oracle_on_our_scores(nb, npost, d, k):
+    rs = np.random.RandomState(nb * 7 + npost)
+    brand = rs.standard_normal((nb, d)).astype(np.float32)
+    posts = rs.standard_normal((npost, d)).astype(np.float32)
+    res, dense, _, _ = _dense_and_topk(brand, posts, k)
+    ref = oref.cal_sim(brand, posts)
+    assert np.abs(dense - ref).max() <= SCORE_ATOL
+    kk = min(k, npost)
+    want_idx = oref.topk_indices(dense, k)
+    got_idx = res["index"].cpu().numpy()
+    got_s = res["scores"].cpu().numpy()
+    assert np.array_equal(got_idx[:, :kk], want_idx)
+    assert np.array_equal(got_s[:, :kk], np.take_along_axis(dense, want_idx, 1))
+    if kk < k:   # padding
+        assert (got_idx[:, kk:] == -1).all() and np.isneginf(got_s[:, kk:]).all()
+
+
+@pytest.mark.parametrize("name", ["lattice", "lattice_small_k"])
+def test_lattice_scores_bit_exact_vs_fp32_reference(golden_dir, name):
+    import os
+    g = np.load(os.path.join(golden_dir, "ranking_%s.npz" % name))
+    nb, lab, w, e, posts = synth.ranking_inputs(name)
+    res, dense, _, _ = _dense_and_topk(w[:nb], posts, 64, labels=lab)
+    assert np.array_equal(dense, g["scores"])            # identical in bf16 and fp32, any order
+    kk = min(64, posts.shape[0])
+    assert np.array_equal(res["index"].cpu().numpy()[:, :kk], oref.topk_indices(g["scores"], 64))
+    ps = res["pos_score"].cpu().numpy()
+    assert np.array_equal(ps, g["scores"][lab, np.arange(len(lab))])
+
+
+def test_heavy_ties_and_index_base():
+    """Quantised scores (few distinct values) -> the tie-break carries the whole ranking."""
+    rs = np.random.RandomState(3)
+    nb, npost, d = 40, 9000, 64
+    brand = synth.lattice(1, nb, d, nnz=16)
+    posts = synth.lattice(2, npost, d, nnz=16)
+    lab = synth.labels(5, npost, nb)
+    base = 1234567
+    res, dense, _, _ = _dense_and_topk(brand, posts, 100, labels=lab, index_base=base)
+    assert len(np.unique(dense)) <= 33
+    want = oref.topk_indices(dense, 100)
+    assert np.array_equal(res["index"].cpu().numpy(), want + base)
+    assert np.array_equal(res["pos_score"].cpu().numpy(), dense[lab, np.arange(npost)])
+
+
+def test_adversarial_increasing_scores():
+    """Scores increase with the post index: every element passes the running threshold."""
+    nb, npost, d = 3, 6000, 64
+    brand = np.zeros((nb, d), np.float32)
+    brand[:, 0] = 1.0
+    posts = np.zeros((npost, d), np.float32)
+    posts[:, 0] = np.linspace(0.1, 1.0, npost)
+    posts[:, 1] = np.sqrt(1.0 - posts[:, 0] ** 2)
+    res, dense, _, _ = _dense_and_topk(brand, posts, 50)
+    assert np.array_equal(res["index"].cpu().numpy(), oref.topk_indices(dense, 50))
+
+
+def test_labels_out_of_range_give_nan_pos_score():
+    rs = np.random.RandomState(9)
+    brand = rs.standard_normal((4, 64)).astype(np.float32)
+    posts = rs.standard_normal((300, 64)).astype(np.float32)
+    lab = rs.randint(0, 4, 300)
+    lab[[3, 77]] = 9
+    lab[5] = -1
+    res, dense, _, _ = _dense_and_topk(brand, posts, 8, labels=lab)
+    ps = res["pos_score"].cpu().numpy()
+    bad = (lab < 0) | (lab >= 4)
+    assert np.isnan(ps[bad]).all()
+    assert np.array_equal(ps[~bad], dense[lab[~bad], np.arange(300)[~bad]])
+
+
+def test_count_pass_matches_oracle():
+    from fancyrec_b200 import ops
+    rs = np.random.RandomState(21)
+    nb, npost, d = 70, 12000, 128
+    brand = synth.lattice(7, nb, d, nnz=16)      # ties matter for the (score, index) comparison
+    posts = synth.lattice(8, npost, d, nnz=16)
+    a, b = operand(brand), operand(posts)
+    dense = ops.score_dense(a, b, d=d).cpu().numpy()
+    tj = rs.randint(0, npost, nb)
+    ts = dense[np.arange(nb), tj].copy()
+    tidx = tj.astype(np.int32)
+    tidx[::9] = -1                                # skipped rows
+    base = 100
+    out = ops.score_count(a, b, to_dev(ts), to_dev(np.where(tidx >= 0, tidx + base, -1).astype(np.int32)), d=d,
+                          index_base=base)
+    got = out.cpu().numpy()
+    for r in range(nb):
+        if tidx[r] < 0:
+            assert got[r] == 0
+            continue
+        order = oref.order_desc(dense[r])
+        assert got[r] == int(np.where(order == tj[r])[0][0])
+
+
+def test_topk_merge_matches_oracle():
+    from fancyrec_b200 import ops
+    rs = np.random.RandomState(31)
+    g, nb, k = 4, 33, 100
+    scores = (rs.randint(-50, 51, size=(nb, 4000)) / 64.0).astype(np.float32)
+    bounds = [0, 1000, 1900, 3100, 4000]
+    sl, il = [], []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        idx = oref.topk_indices(scores[:, a:b], k) + a
+        il.append(idx.astype(np.int32))
+        sl.append(np.take_along_axis(scores, idx, 1))
+    il[2][:, -7:] = -1                       # padding entries are ignored
+    ws, wi = oref.merge_topk(sl, il, k)
+    gs, gi = ops.topk_merge(to_dev(np.stack(sl)), to_dev(np.stack(il)), k)
+    assert np.array_equal(gi.cpu().numpy(), wi.astype(np.int32))
+    assert np.array_equal(gs.cpu().numpy(), ws)
+
+
+def test_bad_arguments_raise():
+    from fancyrec_b200 import _lib, ops
+    a = torch.zeros((4, 64), dtype=torch.bfloat16, device=dev())
+    with pytest.raises(_lib.FrxError):
+        ops.score_topk(a, a, 2000)                       # k > 1024
+    with pytest.raises(_lib.FrxError):
+        ops.score_topk(a.cpu(), a, 4)                    # no CPU path
