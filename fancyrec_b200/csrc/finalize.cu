@@ -209,6 +209,7 @@ int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_
                        int64_t n_posts, int dv, int dt, int flags, float* out_f32, uint16_t* out_bf16,
                        int64_t ld_bf16, void* stream) {
   using namespace frx;
+  if (n_posts == 0) return FRX_OK;
   FRX_CHECK_ARG(visual != nullptr && dv > 0, "frx_finalize_posts: visual is NULL or dv <= 0");
   FRX_CHECK_ARG(n_posts >= 0 && dt >= 0, "frx_finalize_posts: negative size");
   FRX_CHECK_ARG((dt == 0) == (text == nullptr), "frx_finalize_posts: text pointer and dt disagree");

@@ -264,7 +264,10 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
               // S[label[j], j]: lane i holds the label of column cbase+i; the owner row is a lane of
               // this warp iff label - (m_tile*128 + q*32) is in [0, 32)
               int tgt = -1;
-              if (lane < nvalid) tgt = P.labels[cbase + lane] - (m_tile * BM + q * 32);
+              if (lane < nvalid) {
+                const int lbl = P.labels[cbase + lane];
+                if (lbl >= 0 && lbl < P.nb) tgt = lbl - (m_tile * BM + q * 32);   // out-of-range labels keep NaN
+              }
               const uint32_t hit = __ballot_sync(0xffffffffu, tgt >= 0 && tgt < 32);
               if (hit) {
 #pragma unroll
@@ -521,6 +524,15 @@ static Plan make_plan(int nb, int64_t n_posts, int k, int mode) {
   return p;
 }
 
+// ---- measurement hook: CUDA events around each score_kernel launch --------------------------
+struct Probe {
+  bool on = false;
+  int n = 0;
+  cudaEvent_t beg[4096], end[4096];
+  bool made[4096] = {};
+};
+static Probe g_probe;
+
 template <int MODE>
 static int launch_score(const uint16_t* a, int64_t ld_a, const uint16_t* b, int64_t ld_b, int nb, int64_t n_posts, int d,
                         const Plan& plan, ScoreParams& P, cudaStream_t st) {
@@ -536,8 +548,22 @@ static int launch_score(const uint16_t* a, int64_t ld_a, const uint16_t* b, int6
   P.num_n_tiles = plan.num_n_tiles;
   P.splits = plan.splits;
   FRX_CUDA(cudaFuncSetAttribute(score_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  const bool probe = g_probe.on && g_probe.n < 4096;
+  const int slot = g_probe.n;
+  if (probe) {
+    if (!g_probe.made[slot]) {
+      FRX_CUDA(cudaEventCreate(&g_probe.beg[slot]));
+      FRX_CUDA(cudaEventCreate(&g_probe.end[slot]));
+      g_probe.made[slot] = true;
+    }
+    FRX_CUDA(cudaEventRecord(g_probe.beg[slot], st));
+  }
   score_kernel<MODE><<<plan.grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
   FRX_LAUNCH_CHECK();
+  if (probe) {
+    FRX_CUDA(cudaEventRecord(g_probe.end[slot], st));
+    g_probe.n = slot + 1;
+  }
   return FRX_OK;
 }
 
@@ -634,6 +660,23 @@ int frx_score_count(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* po
   P.thr_index = thr_index;
   P.count_out = count_out;
   return launch_score<MODE_COUNT>(brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, plan, P, (cudaStream_t)stream);
+}
+
+int frx_probe_enable(int on) {
+  frx::g_probe.on = on != 0;
+  frx::g_probe.n = 0;
+  return FRX_OK;
+}
+
+int frx_probe_read(float* host_ms_out, int max) {
+  using namespace frx;
+  int n = g_probe.n < max ? g_probe.n : max;
+  for (int i = 0; i < n; ++i) {
+    FRX_CUDA(cudaEventSynchronize(g_probe.end[i]));
+    FRX_CUDA(cudaEventElapsedTime(host_ms_out + i, g_probe.beg[i], g_probe.end[i]));
+  }
+  g_probe.n = 0;
+  return n;
 }
 
 int frx_topk_merge(const float* in_scores, const int32_t* in_index, int g, int nb, int k_in, float* out_scores,

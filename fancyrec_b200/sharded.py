@@ -1,0 +1,113 @@
+"""Post-sharded evaluation across the GPUs of one box.
+
+Posts are independent columns of the score matrix: rank r owns the contiguous range
+[NP*r/G, NP*(r+1)/G) (global index = offset + local, so the (score desc, index asc) comparator is
+shard-invariant) and the small brand operand is replicated.  Each rank runs the fused score + top-k
+kernel on its shard; the only data-path exchange is ONE all-gather of the per-brand candidate lists
+([NB, k] x (fp32 score, int32 global index)) followed by a merge with the same comparator, plus
+NB-length reductions of the integer statistics.  One process per GPU, torch.distributed (NCCL over
+NVLink on the box, gloo in the CPU tests).
+
+`kernels` is the provider of the device steps (default: fancyrec_b200.ops, i.e. libfrx_b200.so); the
+CPU tests inject an oracle-backed provider to exercise the exchange logic without a GPU.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops as _ops
+
+
+def shard_bounds(n_posts, world, rank):
+    return n_posts * rank // world, n_posts * (rank + 1) // world
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def _all_gather_stack(t, group=None):
+    """[n, ...] per rank -> [G, n, ...] (rank-major), one all-gather."""
+    world, _ = _world(group)
+    flat = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(flat, t.contiguous(), group=group)
+    return flat.view((world,) + tuple(t.shape))
+
+
+def gather_lists(scores, index, group=None):
+    """[NB, k] per rank -> ([G, NB, k] scores, [G, NB, k] index), identical on every rank."""
+    world, _ = _world(group)
+    if world == 1:
+        return scores.unsqueeze(0), index.unsqueeze(0)
+    return _all_gather_stack(scores, group), _all_gather_stack(index, group)
+
+
+def gather_labels(labels_local, n_posts, group=None):
+    """Concatenate the label shards in rank order -> [n_posts] on every rank."""
+    world, _ = _world(group)
+    if world == 1:
+        return labels_local
+    sizes = [shard_bounds(n_posts, world, r)[1] - shard_bounds(n_posts, world, r)[0] for r in range(world)]
+    width = max(sizes)                       # ragged shards are padded to a common width for the collective
+    padded = torch.zeros(width, dtype=labels_local.dtype, device=labels_local.device)
+    padded[:labels_local.numel()] = labels_local
+    stacked = _all_gather_stack(padded, group)
+    return torch.cat([stacked[r, :sizes[r]] for r in range(world)])
+
+
+def global_best(best_score, best_index, group=None):
+    """Per brand, the best positive over all shards under (score desc, index asc); index < 0 = none."""
+    world, _ = _world(group)
+    if world == 1:
+        return best_score, best_index
+    gs = _all_gather_stack(best_score, group)
+    gi = _all_gather_stack(best_index, group)
+    valid = gi >= 0
+    s = torch.where(valid, gs, torch.full_like(gs, float("-inf")))
+    top = s.max(dim=0).values
+    big = torch.iinfo(gi.dtype).max
+    cand = torch.where(valid & (s == top.unsqueeze(0)), gi, torch.full_like(gi, big))
+    idx = cand.min(dim=0).values
+    none = ~valid.any(dim=0)
+    idx = torch.where(none, torch.full_like(idx, -1), idx)
+    return top, idx
+
+
+def all_sum(t, group=None):
+    world, _ = _world(group)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def sharded_rank_statistics(brand_op, post_op_local, labels_local, d, k, n_posts_total, group=None,
+                            kernels=_ops, workspace=None):
+    """Device statistics of the WHOLE job from this rank's shard.  Returns the same dict layout as
+    ranking.device_rank_statistics (want_auc=False flavour), identical on every rank."""
+    world, rank = _world(group)
+    lo, hi = shard_bounds(n_posts_total, world, rank)
+    assert post_op_local.shape[0] == hi - lo == labels_local.numel()
+    nb = brand_op.shape[0]
+    k = max(int(k), 64)                            # NDCG@50 reads 50 relevance bits per brand
+    res = kernels.score_topk(brand_op, post_op_local, k, d=d, labels=labels_local, index_base=lo,
+                             workspace=workspace)
+    n_pos_l, best_s_l, best_i_l = kernels.label_stats(labels_local, res["pos_score"], nb, lo)
+    gs, gi = gather_lists(res["scores"], res["index"], group)
+    if world > 1:
+        top_s, top_i = kernels.topk_merge(gs, gi, k)
+    else:
+        top_s, top_i = res["scores"], res["index"]
+    n_pos = all_sum(n_pos_l.clone(), group)
+    best_s, best_i = global_best(best_s_l, best_i_l, group)
+    labels_all = gather_labels(labels_local, n_posts_total, group)
+    hit_mask, first_in_list = kernels.rank_from_topk(top_i, labels_all, 0)
+    missing = (first_in_list < 0) & (n_pos > 0)
+    before = torch.zeros(nb, dtype=torch.int64, device=post_op_local.device)
+    if bool(missing.any().item()):                 # same decision on every rank (inputs are global)
+        thr_index = torch.where(missing, best_i, torch.full_like(best_i, -1))
+        kernels.score_count(brand_op, post_op_local, best_s, thr_index, d=d, index_base=lo, out=before)
+        all_sum(before, group)
+    return dict(topk_scores=top_s, topk_index=top_i, n_pos=n_pos, best_score=best_s, best_index=best_i,
+                hit_mask=hit_mask, first_in_list=first_in_list, before_first=before,
+                before_first_valid=missing, workspace=res.get("workspace"))

@@ -194,6 +194,15 @@ int frx_contrastive_fwd_bwd(const float* brand, const float* post, int b, int d,
 /* F.normalize(post) rows (eps 1e-12), what ContrastiveLoss enqueues (loss_ctrs.py:195,200). */
 int frx_normalize_rows(const float* x, int rows, int d, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Measurement hook (bench.py roofline leg): when enabled, every score kernel launch (top-k, dense,
+ * count mode) is bracketed by a pair of CUDA events on its own stream.  frx_probe_read synchronises
+ * the recorded events and returns up to `max` per-launch durations in milliseconds (oldest first)
+ * and clears the log.  Off by default; at most 4096 launches are logged.
+ */
+int frx_probe_enable(int on);
+int frx_probe_read(float* host_ms_out, int max);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,3 +14,11 @@ def to_dev(a):
 def operand(x_np, final_norm=True):
     from fancyrec_b200 import ranking
     return ranking.to_operand(to_dev(x_np.astype(np.float32)), final_norm=final_norm)
+
+
+def score_atol(d):
+    """Stated score tolerance for bf16 operands with fp32 accumulation, on the cosine scale (|s| <= 1):
+    1e-3 at the embedding sizes the configs name (D >= 256; observed ~2e-4 at D = 3072).  Rounding each
+    unit-norm operand to bf16 (unit round-off 2^-9) perturbs a dot product by at most 2 * 2^-9, which is
+    the bound used for toy dimensions where the errors do not average out."""
+    return 1e-3 if d >= 256 else 2.0 ** -8

@@ -9,7 +9,7 @@ import torch
 from oracle import embed as oembed
 from oracle import ranking as oref
 from oracle import synth
-from tests.gpu_util import dev, to_dev
+from tests.gpu_util import dev, score_atol, to_dev
 
 pytestmark = pytest.mark.gpu
 
@@ -114,7 +114,7 @@ def test_test_post_ranking_dropin(golden_dir, name):
     brand = evaluator.brand_matrix(mdl, nb)
     np.testing.assert_allclose(brand.cpu().numpy(), g["brand"], rtol=1e-5, atol=1e-6)
     ours = evaluator.cal_sim(brand, post_t).cpu().numpy()
-    assert np.abs(ours - g["scores"]).max() <= 1e-3
+    assert np.abs(ours - g["scores"]).max() <= score_atol(posts.shape[1])
     assert got == tuple(float(x) for x in oref.rank_metrics_vec(ours, lab))
     if name.startswith("lattice"):
         assert np.array_equal(ours, g["scores"])
@@ -134,7 +134,7 @@ def test_rank_statistics_bit_exact_medium(want_auc):
     nb, npost, d = 37, 30000, 256
     brand = rs.standard_normal((nb, d)).astype(np.float32)
     lab = synth.labels(78, npost, nb, empty_brands=(3, 20))
-    posts = synth.planted_posts(79, brand, lab, signal=0.02)
+    posts = synth.planted_posts(79, brand, lab, signal=0.0)   # pure noise: first positives land deep
     result, stats, dev_stats = ranking.rank_posts(to_dev(brand), to_dev(posts), to_dev(lab), want_auc=want_auc)
     ours = ops.score_dense(ranking.to_operand(to_dev(brand)), ranking.to_operand(to_dev(posts)), d=d).cpu().numpy()
     ost = oref.rank_stats(ours, lab)
@@ -169,7 +169,7 @@ def test_l2norm_and_cal_sim_api():
     np.testing.assert_allclose(model.l2norm(to_dev(x)).cpu().numpy(), oref.l2norm(x), rtol=RTOL, atol=1e-7)
     s = evaluator.cal_sim(to_dev(y), to_dev(x))
     assert s.shape == (7, 33) and s.dtype == torch.float32 and s.is_cuda
-    assert np.abs(s.cpu().numpy() - oref.cal_sim(y, x)).max() <= 1e-3
+    assert np.abs(s.cpu().numpy() - oref.cal_sim(y, x)).max() <= score_atol(100)
     assert evaluator.random_sim(3, 5).shape == (3, 5)
 
 

@@ -10,11 +10,10 @@ import torch
 
 from oracle import ranking as oref
 from oracle import synth
-from tests.gpu_util import dev, operand, to_dev
+from tests.gpu_util import dev, operand, score_atol, to_dev
 
 pytestmark = pytest.mark.gpu
 
-SCORE_ATOL = 1e-3   # stated tolerance for bf16 inputs (north_star), cosine scale |s| <= 1
 
 
 def _dense_and_topk(brand, posts, k, labels=None, index_base=0):
@@ -38,7 +37,7 @@ def test_topk_matches_oracle_on_our_scores(nb, npost, d, k):
     posts = rs.standard_normal((npost, d)).astype(np.float32)
     res, dense, _, _ = _dense_and_topk(brand, posts, k)
     ref = oref.cal_sim(brand, posts)
-    assert np.abs(dense - ref).max() <= SCORE_ATOL
+    assert np.abs(dense - ref).max() <= score_atol(d)
     kk = min(k, npost)
     want_idx = oref.topk_indices(dense, k)
     got_idx = res["index"].cpu().numpy()
