@@ -202,11 +202,16 @@ def run_ours(args):
     ev.lib.frx_probe_enable(1)
     beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier_sync(world)
+    profile_range = bool(os.environ.get("FRX_PROFILE_RANGE"))   # ncu --profile-from-start off
+    if profile_range:
+        torch.cuda.profiler.start()
     beg.record()
     for _ in range(args.steps):
         result, st = ev.step(w, e, labels, visual, text)
     end.record()
     barrier_sync(world)
+    if profile_range:
+        torch.cuda.profiler.stop()
     ms_total = max_over_ranks(beg.elapsed_time(end), dev, world)
     clocks = sampler.stop() if rank == 0 else None
     buf = (torch.zeros(4096, dtype=torch.float32)).numpy()
