@@ -142,6 +142,107 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams P)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Register-resident variant for rows of up to NV*128 floats (the configs' 1024 / 2048 / 3072):
+// ONE WARP per post row, the whole row lives in registers (NV float4 per lane), every load of a row
+// (or of one frame of it) is issued before the first use -> up to NV 128-bit loads in flight per lane,
+// no shared memory, no block barriers; reductions are warp shuffles.  This is the HBM-roofline path.
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256) finalize_warp_kernel(FinalizeParams P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int d = P.dv + P.dt;
+  const bool vn = (P.flags & FRX_VISUAL_NORM) != 0, tn = (P.flags & FRX_TEXT_NORM) != 0 && P.dt > 0;
+  const bool fn = (P.flags & FRX_FINAL_NORM) != 0;
+  for (int64_t p = wid; p < P.n_posts; p += nwarps) {
+    float4 x[NV];
+    if (P.row_ptr == nullptr) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        x[i] = c < P.dv ? __ldg(reinterpret_cast<const float4*>(P.visual + p * P.dv + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      const int64_t r0 = P.row_ptr[p], r1 = P.row_ptr[p + 1];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int64_t r = r0; r < r1; ++r) {           // frame order = the reference's summation order
+        const int64_t src = P.row_idx ? (int64_t)P.row_idx[r] : r;
+        float4 f[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = (i * 32 + lane) * 4;
+          f[i] = c < P.dv ? __ldg(reinterpret_cast<const float4*>(P.visual + src * P.dv + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { x[i].x += f[i].x; x[i].y += f[i].y; x[i].z += f[i].z; x[i].w += f[i].w; }
+      }
+      const float nf = (float)(r1 - r0);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if ((i * 32 + lane) * 4 < P.dv) { x[i].x /= nf; x[i].y /= nf; x[i].z /= nf; x[i].w /= nf; }
+      }
+    }
+    if (P.dt > 0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c >= P.dv && c < d) x[i] = __ldg(reinterpret_cast<const float4*>(P.text + p * P.dt + (c - P.dv)));
+      }
+    }
+    float ssv = 0.f, sst = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const float q = x[i].x * x[i].x + x[i].y * x[i].y + x[i].z * x[i].z + x[i].w * x[i].w;
+      if (c < P.dv) ssv += q; else if (c < d) sst += q;
+    }
+    ssv = warp_sum(ssv);
+    sst = warp_sum(sst);
+    float total = ssv + sst;
+    if (vn || tn) {
+      const float nv = vn ? sqrtf(ssv) : 1.f, nt = tn ? sqrtf(sst) : 1.f;
+      float s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < d) {
+          const float dn = c < P.dv ? nv : nt;
+          if (c < P.dv ? vn : tn) { x[i].x /= dn; x[i].y /= dn; x[i].z /= dn; x[i].w /= dn; }
+          s2 += x[i].x * x[i].x + x[i].y * x[i].y + x[i].z * x[i].z + x[i].w * x[i].w;
+        }
+      }
+      total = warp_sum(s2);
+    }
+    const float nrm = sqrtf(total);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        float4 a = x[i];
+        if (fn) { a.x /= nrm; a.y /= nrm; a.z /= nrm; a.w /= nrm; }
+        if (P.out_f32) *reinterpret_cast<float4*>(P.out_f32 + p * d + c) = a;
+        if (P.out_bf16) Vec<4>::st_bf16(P.out_bf16 + p * P.ld_bf16 + c, a);
+      }
+    }
+    if (P.out_bf16) {
+      for (int64_t c = d + lane * 4; c < P.ld_bf16; c += 128)   // zero padding (d and ld are multiples of 4)
+        *reinterpret_cast<uint2*>(P.out_bf16 + p * P.ld_bf16 + c) = make_uint2(0u, 0u);
+    }
+  }
+}
+
+template <int NV>
+static void launch_finalize_warp(const FinalizeParams& P, cudaStream_t st) {
+  const int64_t warps_needed = P.n_posts;
+  const int64_t max_blocks = (int64_t)num_sms() * 8;
+  int64_t blocks = (warps_needed + 7) / 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  finalize_warp_kernel<NV><<<(int)blocks, 256, 0, st>>>(P);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Brand embedding: out[i, :] = (1/A) sum_a W[ids[i], a] * E[a, :]   fp32 FMA, 64x64x16 smem tiles.
 // NB is at most ~10k and A = 2000, D <= 3072: at most 1.2e11 flop, a few ms once per evaluation.
 // ---------------------------------------------------------------------------------------------
@@ -227,7 +328,12 @@ int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_
                    aligned16(out_bf16);
   int grid = (int)(n_posts < (int64_t)num_sms() * 8 ? n_posts : (int64_t)num_sms() * 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (vec) {
+  if (vec && d <= 4096 && ld_bf16 % 4 == 0) {
+    if (d <= 1024) launch_finalize_warp<8>(P, st);
+    else if (d <= 2048) launch_finalize_warp<16>(P, st);
+    else if (d <= 3072) launch_finalize_warp<24>(P, st);
+    else launch_finalize_warp<32>(P, st);
+  } else if (vec) {
     if (smem > 48 * 1024) FRX_CUDA(cudaFuncSetAttribute(finalize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     finalize_kernel<4><<<grid, kFinThreads, smem, st>>>(P);
   } else {

@@ -32,8 +32,9 @@ constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int NUM_THREADS = 256;
-constexpr int EPI_WARP0 = 4;                 // warps 4..7 -> TMEM lane quarters 0..3
+constexpr int EPI_WARP0 = 4;                 // warps 4..11: lane quarter = warp % 4, column half = (warp-4)/4
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (EPI_WARP0 + NUM_EPI_WARPS) * 32;   // 384
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_MERGE_KEYS = 16384;
 
@@ -47,8 +48,9 @@ struct ScoreParams {
   int64_t index_base;
   // TOPK
   int k, cap, keep_limit;
-  unsigned long long* part_keys;   // [items][128][cap]
-  int* part_cnt;                   // [items][128]
+  unsigned long long* part_keys;   // [items][2 column halves][128][cap]
+  int* part_cnt;                   // [items][2][128]
+  uint32_t* row_thr;               // [nb] best published lower bound of each row's k-th best score (ordered)
   const int32_t* labels;
   float* pos_score;
   // DENSE
@@ -64,79 +66,125 @@ struct SmemTail {
   uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
-  uint32_t hist[4][256];
+  uint32_t hist[NUM_EPI_WARPS][256];
 };
 constexpr size_t SMEM_BYTES = 1024 /* alignment slack */ + (size_t)STAGES * STAGE_BYTES + sizeof(SmemTail);
 
 // ---------------------------------------------------------------------------------------------
-// Warp-cooperative radix select on one row's candidate buffer (global memory, L2-resident).
+// Warp-cooperative MSB-first radix select over one row's candidate keys.
 // Keeps the best `k` keys (or, when !exact, between k and keep_limit keys as soon as a digit boundary
 // allows it), compacts them to buf[0..kept) and returns kept; *thr_out = a score that every kept key
 // reaches and no dropped key exceeds (the new append threshold).
+// KPL > 0: the row's keys (n <= 32*KPL) are loaded ONCE into registers (KPL independent 8-byte loads in
+// flight per lane) and every pass runs from registers.  KPL == 0: generic path for large buffers, keys
+// re-read from L2 each pass in batches of 8 independent loads.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void select_digit(uint32_t* hist, int lane, int need, int& digit, int& above, int& bucket) {
+  uint32_t h[8], lsum = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { h[i] = hist[lane * 8 + i]; lsum += h[i]; }
+  uint32_t suf = lsum;                         // inclusive suffix sum over lanes (higher lane = higher digits)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_down_sync(0xffffffffu, suf, o);
+    if (lane + o < 32) suf += t;
+  }
+  const bool cross = suf >= (uint32_t)need && (suf - lsum) < (uint32_t)need;
+  const int cl = __ffs(__ballot_sync(0xffffffffu, cross)) - 1;   // exactly one lane crosses
+  int dg = 0, ab = 0, bc = 0;
+  if (lane == cl) {
+    uint32_t acc = suf - lsum;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      if (bc == 0) {
+        if (acc + h[i] >= (uint32_t)need) { dg = lane * 8 + i; ab = (int)acc; bc = (int)h[i]; }
+        else acc += h[i];
+      }
+    }
+  }
+  digit = __shfl_sync(0xffffffffu, dg, cl);
+  above = __shfl_sync(0xffffffffu, ab, cl);
+  bucket = __shfl_sync(0xffffffffu, bc, cl);
+}
+
+template <int KPL>
 __device__ __forceinline__ int warp_select(unsigned long long* buf, int n, int k, int keep_limit, bool exact,
                                            uint32_t* hist, float* thr_out) {
   const int lane = threadIdx.x & 31;
+  unsigned long long keys[KPL > 0 ? KPL : 1];
+  if (KPL > 0) {
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      const int i = j * 32 + lane;
+      keys[j] = i < n ? __ldcg(buf + i) : 0ull;    // 0 is below every real key and never matches a prefix > 0
+    }
+  }
   unsigned long long prefix = 0;
   int need = k, above_total = 0, shift = 56, bucket = 0;
   for (int pass = 0; pass < 8; ++pass, shift -= 8) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) hist[lane * 8 + i] = 0;
     __syncwarp();
-    for (int i = lane; i < n; i += 32) {
-      unsigned long long key = __ldcg(buf + i);
-      if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
-    }
-    __syncwarp();
-    uint32_t h[8], lsum = 0;
+    if (KPL > 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { h[i] = hist[lane * 8 + i]; lsum += h[i]; }
-    // inclusive suffix sum over lanes (higher lane = higher digits)
-    uint32_t suf = lsum;
+      for (int j = 0; j < KPL; ++j) {
+        const unsigned long long key = keys[j];
+        if (j * 32 + lane < n && (pass == 0 || (key >> (shift + 8)) == prefix))
+          atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
+      }
+    } else {
+      for (int base = 0; base < n; base += 256) {
+        unsigned long long kk[8];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_down_sync(0xffffffffu, suf, o);
-      if (lane + o < 32) suf += t;
-    }
-    const bool cross = suf >= (uint32_t)need && (suf - lsum) < (uint32_t)need;
-    const uint32_t cm = __ballot_sync(0xffffffffu, cross);
-    const int cl = __ffs(cm) - 1;            // exactly one lane crosses (need <= matching count)
-    int digit = 0, above = 0, bcnt = 0;
-    if (lane == cl) {
-      uint32_t acc = suf - lsum;             // matching keys in higher lanes
+        for (int j = 0; j < 8; ++j) { const int i = base + j * 32 + lane; kk[j] = i < n ? __ldcg(buf + i) : 0ull; }
 #pragma unroll
-      for (int i = 7; i >= 0; --i) {
-        if (bcnt == 0) {
-          if (acc + h[i] >= (uint32_t)need) { digit = lane * 8 + i; above = (int)acc; bcnt = (int)h[i]; }
-          else acc += h[i];
+        for (int j = 0; j < 8; ++j) {
+          if (base + j * 32 + lane < n && (pass == 0 || (kk[j] >> (shift + 8)) == prefix))
+            atomicAdd(&hist[(uint32_t)(kk[j] >> shift) & 255u], 1u);
         }
       }
     }
-    digit = __shfl_sync(0xffffffffu, digit, cl);
-    above = __shfl_sync(0xffffffffu, above, cl);
-    bucket = __shfl_sync(0xffffffffu, bcnt, cl);
+    __syncwarp();
+    int digit, above;
+    select_digit(hist, lane, need, digit, above, bucket);
     above_total += above;
     need -= above;
     prefix = (prefix << 8) | (unsigned long long)digit;
-    if (!exact && above_total + bucket <= keep_limit) { break; }
-    if (pass == 7) break;
+    if ((!exact && above_total + bucket <= keep_limit) || pass == 7) break;
   }
-  if (shift < 0) shift = 0;
   const unsigned long long thr_key = prefix << shift;   // smallest key of the boundary bucket
   int out = 0;
-  for (int base = 0; base < n; base += 32) {
-    const int i = base + lane;
-    unsigned long long key = i < n ? __ldcg(buf + i) : 0ull;
-    const bool keep = i < n && key >= thr_key;
-    const uint32_t m = __ballot_sync(0xffffffffu, keep);
-    if (keep) buf[out + __popc(m & ((1u << lane) - 1u))] = key;
-    out += __popc(m);
-    __syncwarp();
+  if (KPL > 0) {
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      if (j * 32 < n) {                                  // warp-uniform
+        const bool keep = (j * 32 + lane < n) && keys[j] >= thr_key;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (keep) buf[out + __popc(m & ((1u << lane) - 1u))] = keys[j];
+        out += __popc(m);
+      }
+    }
+  } else {
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const unsigned long long key = i < n ? __ldcg(buf + i) : 0ull;
+      const bool keep = i < n && key >= thr_key;
+      const uint32_t m = __ballot_sync(0xffffffffu, keep);
+      if (keep) buf[out + __popc(m & ((1u << lane) - 1u))] = key;   // out + rank <= i: never clobbers unread keys
+      out += __popc(m);
+      __syncwarp();
+    }
   }
   float t = ordered_to_score((uint32_t)(thr_key >> 32));
   if (t != t) t = -INFINITY;   // bucket edge decoded to a NaN pattern
   *thr_out = t;
   return out;
+}
+
+__device__ __forceinline__ int select_dispatch(int cap, unsigned long long* buf, int n, int k, int keep_limit,
+                                               bool exact, uint32_t* hist, float* thr_out) {
+  if (cap <= 1024) return warp_select<32>(buf, n, k, keep_limit, exact, hist, thr_out);
+  return warp_select<0>(buf, n, k, keep_limit, exact, hist, thr_out);
 }
 
 template <int MODE>
@@ -155,7 +203,7 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&tail->full[s]), 1); mbar_init(smem_u32(&tail->empty[s]), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tail->tmem_full[s]), 1); mbar_init(smem_u32(&tail->tmem_empty[s]), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tail->tmem_full[s]), 1); mbar_init(smem_u32(&tail->tmem_empty[s]), NUM_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(&tail->tmem_base));
@@ -218,9 +266,13 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     }
   } else if (warp >= EPI_WARP0) {
     // =========================== epilogue ===========================
-    const int q = warp - EPI_WARP0;                  // TMEM lane quarter (== warp % 4)
+    // 8 warps: lane quarter q = warp % 4 (TMEM lanes 32q..32q+31 = brand rows), column half h.
+    const int q = warp & 3;
+    const int h = (warp - EPI_WARP0) >> 2;
+    const int ew = warp - EPI_WARP0;
     const int row_in_tile = q * 32 + lane;
-    uint32_t* hist = tail->hist[q];
+    constexpr int CHUNKS = BN / 2 / 32;              // 4 chunks of 32 columns per warp per tile
+    uint32_t* hist = tail->hist[ew];
     int as = 0; uint32_t aphase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int m_tile = item % P.num_m_tiles, split = item / P.num_m_tiles;
@@ -231,19 +283,33 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       // per-row state
       float thr = row_ok ? -INFINITY : INFINITY;     // TOPK: append threshold
       int cnt = 0;                                   // TOPK: candidates buffered
+      const size_t part = ((size_t)item * 2 + h) * BM;            // candidate lists of this (item, half)
       unsigned long long* rowbuf = nullptr;
       float ts = 0.f; int32_t ti = -1; unsigned long long ccount = 0;
-      if (MODE == MODE_TOPK) rowbuf = P.part_keys + ((size_t)item * BM + row_in_tile) * P.cap;
+      if (MODE == MODE_TOPK) rowbuf = P.part_keys + (part + row_in_tile) * P.cap;
       if (MODE == MODE_COUNT && row_ok) { ts = P.thr_score[row]; ti = P.thr_index[row]; }
 
       for (int64_t t = t0; t < t1; ++t) {
+        const int64_t col0 = t * BN + h * (BN / 2);
+        // issued before the accumulator wait so that their latency is hidden: the labels of this warp's
+        // 128 columns and the row's global threshold (best lower bound published by any CTA so far)
+        int lab[CHUNKS];
+        if (MODE == MODE_TOPK) {
+          if (P.labels != nullptr) {
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+              const int64_t j = col0 + c * 32 + lane;
+              lab[c] = j < P.n_posts ? __ldg(P.labels + j) : -1;
+            }
+          }
+          if (row_ok) thr = fmaxf(thr, ordered_to_score(__ldcg(P.row_thr + row)));
+        }
         mbar_wait(smem_u32(&tail->tmem_full[as]), aphase);
         tc_fence_after();
-        const int64_t col0 = t * BN;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < CHUNKS; ++c) {
           uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + h * (BN / 2) + c * 32), v);
           tmem_ld_wait();
           const int64_t cbase = col0 + c * 32;
           const int64_t rem = P.n_posts - cbase;
@@ -251,23 +317,48 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           if (nvalid == 0) continue;                 // warp-uniform
 
           if (MODE == MODE_TOPK) {
-            const uint32_t gbase = (uint32_t)(P.index_base + cbase);
+            // fast path: does any lane hold a score that reaches its row's threshold?
+            float mx = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float s = __uint_as_float(v[i]);
-              if (i < nvalid && s >= thr) {
-                rowbuf[cnt] = make_key(s, gbase + i);
-                ++cnt;
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (i < nvalid) ? __uint_as_float(v[i]) : -INFINITY);
+            if (__any_sync(0xffffffffu, mx >= thr)) {
+              const uint32_t gbase = (uint32_t)(P.index_base + cbase);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float s = __uint_as_float(v[i]);
+                if (i < nvalid && s >= thr) {
+                  rowbuf[cnt] = make_key(s, gbase + i);
+                  ++cnt;
+                }
+              }
+              // keep room for the next 32-column chunk
+              uint32_t full = __ballot_sync(0xffffffffu, cnt > P.cap - 32);
+              if (full) {
+                __syncwarp();
+                while (full) {
+                  const int l = __ffs(full) - 1;
+                  full &= full - 1;
+                  const int n = __shfl_sync(0xffffffffu, cnt, l);
+                  unsigned long long* b = P.part_keys + (part + q * 32 + l) * P.cap;
+                  float nthr;
+                  const int kept = select_dispatch(P.cap, b, n, P.k, P.keep_limit, false, hist, &nthr);
+                  if (lane == l) {
+                    cnt = kept;
+                    thr = fmaxf(thr, nthr);
+                    atomicMax(P.row_thr + row, score_to_ordered(thr));   // publish: valid for every CTA of this row
+                  }
+                }
+                __syncwarp();
               }
             }
             if (P.labels != nullptr) {
               // S[label[j], j]: lane i holds the label of column cbase+i; the owner row is a lane of
               // this warp iff label - (m_tile*128 + q*32) is in [0, 32)
+              int lbl = -1;
+#pragma unroll
+              for (int cc = 0; cc < CHUNKS; ++cc) if (cc == c) lbl = lab[cc];
               int tgt = -1;
-              if (lane < nvalid) {
-                const int lbl = P.labels[cbase + lane];
-                if (lbl >= 0 && lbl < P.nb) tgt = lbl - (m_tile * BM + q * 32);   // out-of-range labels keep NaN
-              }
+              if (lbl >= 0 && lbl < P.nb) tgt = lbl - (m_tile * BM + q * 32);   // out-of-range labels keep NaN
               const uint32_t hit = __ballot_sync(0xffffffffu, tgt >= 0 && tgt < 32);
               if (hit) {
 #pragma unroll
@@ -278,21 +369,6 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                   }
                 }
               }
-            }
-            // keep room for the next 32-column chunk
-            uint32_t full = __ballot_sync(0xffffffffu, cnt > P.cap - 32);
-            if (full) {
-              __syncwarp();
-              while (full) {
-                const int l = __ffs(full) - 1;
-                full &= full - 1;
-                const int n = __shfl_sync(0xffffffffu, cnt, l);
-                unsigned long long* b = P.part_keys + ((size_t)item * BM + q * 32 + l) * P.cap;
-                float nthr;
-                const int kept = warp_select(b, n, P.k, P.keep_limit, false, hist, &nthr);
-                if (lane == l) { cnt = kept; thr = fmaxf(thr, nthr); }
-              }
-              __syncwarp();
             }
           } else if (MODE == MODE_DENSE) {
             if (row_ok) {
@@ -337,12 +413,12 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           const int l = __ffs(over) - 1;
           over &= over - 1;
           const int n = __shfl_sync(0xffffffffu, cnt, l);
-          unsigned long long* b = P.part_keys + ((size_t)item * BM + q * 32 + l) * P.cap;
+          unsigned long long* b = P.part_keys + (part + q * 32 + l) * P.cap;
           float nthr;
-          const int kept = warp_select(b, n, P.k, P.k, true, hist, &nthr);
-          if (lane == l) cnt = kept;
+          const int kept = select_dispatch(P.cap, b, n, P.k, P.k, true, hist, &nthr);
+          if (lane == l) { cnt = kept; atomicMax(P.row_thr + row, score_to_ordered(fmaxf(thr, nthr))); }
         }
-        P.part_cnt[(size_t)item * BM + row_in_tile] = cnt;
+        P.part_cnt[part + row_in_tile] = cnt;
       } else if (MODE == MODE_COUNT) {
         if (row_ok && ti >= 0 && ccount) atomicAdd(P.count_out + row, ccount);
       }
@@ -389,22 +465,23 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long
                                                              int splits, int cap, int k, float* __restrict__ out_s,
                                                              int32_t* __restrict__ out_i) {
   extern __shared__ unsigned long long skeys[];
-  __shared__ int offs[1025];
+  __shared__ int offs[2049];
   const int b = blockIdx.x, m_tile = b / BM, r = b % BM;
+  const int lists = splits * 2;                 // (split, column half) -> list (split*num_m_tiles + m_tile)*2 + half
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int s = 0; s < splits; ++s) {
+    for (int s = 0; s < lists; ++s) {
       offs[s] = acc;
-      acc += part_cnt[((size_t)s * num_m_tiles + m_tile) * BM + r];
+      acc += part_cnt[(((size_t)(s >> 1) * num_m_tiles + m_tile) * 2 + (s & 1)) * BM + r];
     }
-    offs[splits] = acc;
+    offs[lists] = acc;
   }
   __syncthreads();
-  const int total = offs[splits];
+  const int total = offs[lists];
   const int np2 = next_pow2(total > 1 ? total : 2);
-  for (int s = 0; s < splits; ++s) {
+  for (int s = 0; s < lists; ++s) {
     const int n = offs[s + 1] - offs[s];
-    const unsigned long long* src = part_keys + (((size_t)s * num_m_tiles + m_tile) * BM + r) * cap;
+    const unsigned long long* src = part_keys + ((((size_t)(s >> 1) * num_m_tiles + m_tile) * 2 + (s & 1)) * BM + r) * cap;
     for (int i = threadIdx.x; i < n; i += blockDim.x) skeys[offs[s] + i] = src[i];
   }
   for (int i = total + threadIdx.x; i < np2; i += blockDim.x) skeys[i] = 0ull;
@@ -491,7 +568,7 @@ static int make_operand_map(CUtensorMap* map, const void* ptr, int64_t rows, int
 struct Plan {
   int num_m_tiles, splits, cap, keep_limit, grid;
   int64_t num_n_tiles;
-  size_t keys_bytes, cnt_bytes;
+  size_t keys_bytes, cnt_bytes, thr_bytes;
 };
 
 static Plan make_plan(int nb, int64_t n_posts, int k, int mode) {
@@ -500,7 +577,7 @@ static Plan make_plan(int nb, int64_t n_posts, int k, int mode) {
   p.num_m_tiles = (nb + BM - 1) / BM;
   p.num_n_tiles = (n_posts + BN - 1) / BN;
   int64_t smax = p.num_n_tiles;
-  if (mode == MODE_TOPK && smax > MAX_MERGE_KEYS / k) smax = MAX_MERGE_KEYS / k;
+  if (mode == MODE_TOPK && smax > MAX_MERGE_KEYS / (2 * k)) smax = MAX_MERGE_KEYS / (2 * k);   // 2 lists per split
   if (smax > 1024) smax = 1024;
   if (smax < 1) smax = 1;
   // pick the split count that fills whole waves of `sms` CTAs; prefer fewer, longer items
@@ -519,8 +596,9 @@ static Plan make_plan(int nb, int64_t n_posts, int k, int mode) {
   while (cap < 4 * k) cap <<= 1;
   p.cap = cap;
   p.keep_limit = k + k / 4;
-  p.keys_bytes = (size_t)items * BM * cap * sizeof(unsigned long long);
-  p.cnt_bytes = (((size_t)items * BM * sizeof(int)) + 255) & ~(size_t)255;
+  p.keys_bytes = (size_t)items * 2 * BM * cap * sizeof(unsigned long long);
+  p.cnt_bytes = (((size_t)items * 2 * BM * sizeof(int)) + 255) & ~(size_t)255;
+  p.thr_bytes = (((size_t)nb * sizeof(uint32_t)) + 255) & ~(size_t)255;
   return p;
 }
 
@@ -587,7 +665,7 @@ size_t frx_score_topk_workspace_bytes(int nb, int64_t n_posts, int d, int k) {
   (void)d;
   if (nb <= 0 || n_posts <= 0 || k <= 0 || k > 1024) return 0;
   frx::Plan p = frx::make_plan(nb, n_posts, k, frx::MODE_TOPK);
-  return p.keys_bytes + p.cnt_bytes + 256;
+  return p.keys_bytes + p.cnt_bytes + p.thr_bytes + 256;
 }
 
 int frx_score_topk(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* post_bf16, int64_t ld_b, int nb,
@@ -603,7 +681,7 @@ int frx_score_topk(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* pos
   FRX_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "frx_score_topk: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   Plan plan = make_plan(nb, n_posts, k, MODE_TOPK);
-  const size_t need = plan.keys_bytes + plan.cnt_bytes + 256;
+  const size_t need = plan.keys_bytes + plan.cnt_bytes + plan.thr_bytes + 256;
   if (workspace == nullptr || workspace_bytes < need) {
     set_error("frx_score_topk: workspace %zu bytes, need %zu", workspace_bytes, need);
     return FRX_E_WORKSPACE;
@@ -614,13 +692,15 @@ int frx_score_topk(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* pos
   P.cap = plan.cap;
   P.keep_limit = plan.keep_limit;
   P.part_cnt = reinterpret_cast<int*>(workspace);
-  P.part_keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(workspace) + plan.cnt_bytes);
+  P.row_thr = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + plan.cnt_bytes);
+  P.part_keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(workspace) + plan.cnt_bytes + plan.thr_bytes);
+  FRX_CUDA(cudaMemsetAsync(P.row_thr, 0, plan.thr_bytes, st));     // ordered 0 = below every score
   P.labels = labels;
   P.pos_score = pos_score;
   if (pos_score) FRX_CUDA(cudaMemsetAsync(pos_score, 0xFF, (size_t)n_posts * sizeof(float), st));   // NaN
   rc = launch_score<MODE_TOPK>(brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, plan, P, st);
   if (rc) return rc;
-  const int total_max = plan.splits * k;
+  const int total_max = plan.splits * 2 * k;
   int np2 = 2;
   while (np2 < total_max) np2 <<= 1;
   const size_t msmem = (size_t)np2 * sizeof(unsigned long long);

@@ -8,7 +8,6 @@ import numpy as np
 import torch
 
 from . import ops
-from .util.ndcg import ndcg_from_hits
 
 HIT_DEPTH = 50          # evaluator.py:120 reads NDCG@50 -> 50 relevance bits per brand
 MIN_TOPK = 64
@@ -85,30 +84,55 @@ def host_statistics(dev_stats, n_posts, want_auc=True):
     return st
 
 
+def _ndcg_rows(hits, n_pos, k, n_posts):
+    """ndcg_at_k (util/ndcg.py:48-78) for every row of a 0/1 `hits` matrix at once.  Row reductions run
+    over the contiguous last axis, so NumPy applies to each row the same pairwise summation it applies
+    to the reference's 1-D np.sum -- results are bit-identical (tests/test_abi.py checks this)."""
+    depth = min(k, n_posts, hits.shape[1])
+    r = np.ascontiguousarray(hits[:, :depth], dtype=np.float64)
+    if depth > 1:
+        disc = np.log2(np.arange(2, depth + 1))
+        dcg = r[:, 0] + np.sum(np.ascontiguousarray(r[:, 1:] / disc), axis=1)
+    else:
+        dcg = r[:, 0].copy()
+    # ideal DCG depends only on min(n_pos, depth): a table of depth + 1 scalars, computed like the reference
+    table = np.zeros(depth + 1, dtype=np.float64)
+    for m in range(1, depth + 1):
+        ideal = np.zeros(depth, dtype=np.float64)
+        ideal[:m] = 1.0
+        table[m] = ideal[0] + (np.sum(ideal[1:] / np.log2(np.arange(2, depth + 1))) if depth > 1 else 0.0)
+    best = table[np.minimum(n_pos, depth)]
+    out = np.zeros(len(n_pos), dtype=np.float64)
+    nz = best != 0
+    out[nz] = dcg[nz] / best[nz]
+    return out
+
+
 def aggregate(stats, n_posts, want_auc=True):
     """evaluator.py:105,115-143 on the integer statistics.  Returns
     (MedR, MeanR, AUC, NDCG@10, NDCG@50, r1, r5, r10); AUC is NaN when want_auc is False."""
-    n_pos = stats["n_pos"]
+    n_pos = np.asarray(stats["n_pos"], dtype=np.int64)
     nb = len(n_pos)
-    ranks = np.zeros(nb)                      # brands without positives keep 0 -> count as recall hits
-    first, aucs, n10, n50 = [], [], [], []
-    for b in range(nb):
-        if n_pos[b] == 0:
-            continue
-        ranks[b] = stats["first_rank"][b]
-        first.append(int(stats["first_rank"][b]))
-        if want_auc:
-            aucs.append(float(np.int64(stats["auc_num"][b])) / (int(n_pos[b]) * (n_posts - int(n_pos[b]))))
-        n10.append(ndcg_from_hits(stats["hits"][b], n_pos[b], 10, n_posts))
-        n50.append(ndcg_from_hits(stats["hits"][b], n_pos[b], 50, n_posts))
-    if not first:
+    has = n_pos > 0
+    if not has.any():
         raise IndexError("no brand has a positive post (the reference fails the same way, evaluator.py:132-134)")
+    first_rank = np.asarray(stats["first_rank"], dtype=np.int64)
+    ranks = np.where(has, first_rank, 0).astype(np.float64)   # brands without positives keep 0 -> recall hits
+    first = first_rank[has]
     r1 = 100.0 * len(np.where(ranks < 1)[0]) / len(ranks)
     r5 = 100.0 * len(np.where(ranks < 5)[0]) / len(ranks)
     r10 = 100.0 * len(np.where(ranks < 10)[0]) / len(ranks)
-    return (np.floor(np.median(tuple(first))), np.floor(np.mean(tuple(first))),
-            np.average(tuple(aucs)) if want_auc else np.float64("nan"),
-            np.average(tuple(n10)), np.average(tuple(n50)), r1, r5, r10)
+    if want_auc:
+        num = np.asarray(stats["auc_num"], dtype=np.int64)[has].astype(np.float64)
+        den = (n_pos[has] * (n_posts - n_pos[has])).astype(np.float64)   # exact below 2^53, as float(int)/int is
+        auc = np.average(num / den)
+    else:
+        auc = np.float64("nan")
+    hits = np.asarray(stats["hits"])[has]
+    n10 = _ndcg_rows(hits, n_pos[has], 10, n_posts)
+    n50 = _ndcg_rows(hits, n_pos[has], 50, n_posts)
+    return (np.floor(np.median(first)), np.floor(np.mean(first)), auc,
+            np.average(n10), np.average(n50), r1, r5, r10)
 
 
 def rank_posts(brand_f32, post_f32, labels, k=MIN_TOPK, want_auc=True):

@@ -88,3 +88,24 @@ def test_aggregate_matches_oracle_on_host():
     got = ranking.aggregate(dict(n_pos=st["n_pos"], first_rank=st["first_rank"], hits=st["hits"],
                                  auc_num=st["auc_num"]), 150, True)
     assert tuple(map(float, got)) == tuple(map(float, oref.rank_metrics_loop(scores, lab)))
+
+
+def test_vectorised_aggregate_is_bit_identical_to_per_brand_reference_calls():
+    """Row-wise np.sum over [NB, 50] == the reference's per-brand 1-D np.sum (pairwise order), and the
+    Python-int AUC division == float64 division, over many random relevance patterns."""
+    import numpy as np
+    from fancyrec_b200 import ranking
+    from oracle import ranking as oref
+    rs = np.random.RandomState(11)
+    for trial in range(20):
+        nb, n_posts = 200, 100000
+        n_pos = rs.randint(0, 300, nb)
+        n_pos[rs.randint(0, nb, 5)] = 0
+        hits = (rs.rand(nb, 50) < rs.rand(nb, 1)).astype(np.uint8)
+        hits[n_pos == 0] = 0
+        first = np.where(n_pos > 0, rs.randint(0, 5000, nb), -1)
+        auc_num = (rs.rand(nb) * n_pos * (n_posts - n_pos)).astype(np.int64)
+        st = dict(n_pos=n_pos.astype(np.int64), first_rank=first.astype(np.int64), hits=hits, auc_num=auc_num)
+        got = ranking.aggregate(st, n_posts, True)
+        want = oref.aggregate(st, n_posts)
+        assert tuple(map(float, got)) == tuple(map(float, want))
