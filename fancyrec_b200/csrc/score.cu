@@ -442,7 +442,7 @@ __device__ void block_bitonic_desc(unsigned long long* keys, int n_pow2) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       __syncthreads();
       for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
-        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));   // stride is a power of two
         const int hi = lo + stride;
         const bool desc = ((lo & size) == 0);
         unsigned long long a = keys[lo], b = keys[hi];
@@ -461,11 +461,13 @@ __device__ __forceinline__ int next_pow2(int v) {
 
 // One block per brand: gather the per-split candidate lists of this row, sort, emit the top-k.
 __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long long* __restrict__ part_keys,
-                                                             const int* __restrict__ part_cnt, int num_m_tiles,
+                                                             const int* __restrict__ part_cnt,
+                                                             const uint32_t* __restrict__ row_thr, int num_m_tiles,
                                                              int splits, int cap, int k, float* __restrict__ out_s,
                                                              int32_t* __restrict__ out_i) {
   extern __shared__ unsigned long long skeys[];
   __shared__ int offs[2049];
+  __shared__ int kept;
   const int b = blockIdx.x, m_tile = b / BM, r = b % BM;
   const int lists = splits * 2;                 // (split, column half) -> list (split*num_m_tiles + m_tile)*2 + half
   if (threadIdx.x == 0) {
@@ -477,13 +479,22 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long
     offs[lists] = acc;
   }
   __syncthreads();
-  const int total = offs[lists];
-  const int np2 = next_pow2(total > 1 ? total : 2);
+  // Only keys that reach the row's final published threshold (a lower bound of the global k-th best
+  // score) can be in the top-k; lists closed early under a weaker threshold shrink to a handful here.
+  if (threadIdx.x == 0) kept = 0;
+  __syncthreads();
+  const uint32_t thr = offs[lists] > k ? row_thr[b] : 0u;
   for (int s = 0; s < lists; ++s) {
     const int n = offs[s + 1] - offs[s];
     const unsigned long long* src = part_keys + ((((size_t)(s >> 1) * num_m_tiles + m_tile) * 2 + (s & 1)) * BM + r) * cap;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) skeys[offs[s] + i] = src[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long key = src[i];
+      if ((uint32_t)(key >> 32) >= thr) skeys[atomicAdd(&kept, 1)] = key;
+    }
   }
+  __syncthreads();
+  const int total = kept;
+  const int np2 = next_pow2(total > 1 ? total : 2);
   for (int i = total + threadIdx.x; i < np2; i += blockDim.x) skeys[i] = 0ull;
   block_bitonic_desc(skeys, np2);
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
@@ -706,7 +717,7 @@ int frx_score_topk(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* pos
   const size_t msmem = (size_t)np2 * sizeof(unsigned long long);
   if (msmem > 48 * 1024)
     FRX_CUDA(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-  merge_partials_kernel<<<nb, 256, msmem, st>>>(P.part_keys, P.part_cnt, plan.num_m_tiles, plan.splits, plan.cap, k,
+  merge_partials_kernel<<<nb, 256, msmem, st>>>(P.part_keys, P.part_cnt, P.row_thr, plan.num_m_tiles, plan.splits, plan.cap, k,
                                                 topk_scores, topk_index);
   FRX_LAUNCH_CHECK();
   if (dense_out) return frx_score_dense(brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, dense_out, ld_dense, stream);
