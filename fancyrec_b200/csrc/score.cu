@@ -468,6 +468,8 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long
   extern __shared__ unsigned long long skeys[];
   __shared__ int offs[2049];
   __shared__ int kept;
+  __shared__ uint32_t hist[256];
+  __shared__ int sel[3];
   const int b = blockIdx.x, m_tile = b / BM, r = b % BM;
   const int lists = splits * 2;                 // (split, column half) -> list (split*num_m_tiles + m_tile)*2 + half
   if (threadIdx.x == 0) {
@@ -479,21 +481,53 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long
     offs[lists] = acc;
   }
   __syncthreads();
-  // Only keys that reach the row's final published threshold (a lower bound of the global k-th best
-  // score) can be in the top-k; lists closed early under a weaker threshold shrink to a handful here.
   if (threadIdx.x == 0) kept = 0;
-  __syncthreads();
-  const uint32_t thr = offs[lists] > k ? row_thr[b] : 0u;
   for (int s = 0; s < lists; ++s) {
     const int n = offs[s + 1] - offs[s];
     const unsigned long long* src = part_keys + ((((size_t)(s >> 1) * num_m_tiles + m_tile) * 2 + (s & 1)) * BM + r) * cap;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned long long key = src[i];
-      if ((uint32_t)(key >> 32) >= thr) skeys[atomicAdd(&kept, 1)] = key;
-    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) skeys[offs[s] + i] = src[i];
   }
   __syncthreads();
-  const int total = kept;
+  int total = offs[lists];
+  // More than k candidates: block-wide MSB-first radix select of the k-th best key (exact), then only the
+  // k survivors are sorted -- instead of bitonic-sorting all splits * 2 * k keys.
+  if (total > k) {
+    unsigned long long prefix = 0;
+    int need = k, shift = 56;
+    for (int pass = 0; pass < 8; ++pass, shift -= 8) {
+      if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+      __syncthreads();
+      for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const unsigned long long key = skeys[i];
+        if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        int digit, above, bucket;
+        select_digit(hist, threadIdx.x, need, digit, above, bucket);
+        if (threadIdx.x == 0) { sel[0] = digit; sel[1] = above; sel[2] = bucket; }
+      }
+      __syncthreads();
+      prefix = (prefix << 8) | (unsigned long long)sel[0];
+      need -= sel[1];
+      const int bucket = sel[2];
+      __syncthreads();
+      if (bucket == 1 || pass == 7) break;        // keys are unique: a singleton bucket pins the k-th key
+    }
+    const unsigned long long thr_key = prefix << shift;
+    // survivors (exactly k) go to the tail region of skeys, then are moved to the front
+    unsigned long long* dst = skeys + total;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const unsigned long long key = skeys[i];
+      if (key >= thr_key) dst[atomicAdd(&kept, 1)] = key;
+    }
+    __syncthreads();
+    const int nk = kept;
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) { const unsigned long long key = dst[i]; skeys[i] = key; }
+    // (reads of dst[i] and writes of skeys[i] never alias: dst starts at total >= nk)
+    __syncthreads();
+    total = nk;
+  }
   const int np2 = next_pow2(total > 1 ? total : 2);
   for (int i = total + threadIdx.x; i < np2; i += blockDim.x) skeys[i] = 0ull;
   block_bitonic_desc(skeys, np2);
@@ -713,8 +747,9 @@ int frx_score_topk(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* pos
   if (rc) return rc;
   const int total_max = plan.splits * 2 * k;
   int np2 = 2;
-  while (np2 < total_max) np2 <<= 1;
-  const size_t msmem = (size_t)np2 * sizeof(unsigned long long);
+  while (np2 < 2 * k) np2 <<= 1;                                 // sort buffer when nothing needs selecting
+  const size_t mkeys = (size_t)(total_max + k) > (size_t)np2 ? (size_t)(total_max + k) : (size_t)np2;
+  const size_t msmem = mkeys * sizeof(unsigned long long);
   if (msmem > 48 * 1024)
     FRX_CUDA(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
   merge_partials_kernel<<<nb, 256, msmem, st>>>(P.part_keys, P.part_cnt, P.row_thr, plan.num_m_tiles, plan.splits, plan.cap, k,
