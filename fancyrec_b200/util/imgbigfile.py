@@ -1,0 +1,79 @@
+"""feature.bin reader with the reference's API (util/imgbigfile.py:5-61) plus the bulk path the
+finalisation kernel wants.
+
+On-disk format (util/imgbigfile.py:7-16, preprocess/txt2bin.py:93-108): `feature.bin` = row-major float32
+[N, ndims], native endian, no header; `shape.txt` = "N ndims"; `id.txt` = names joined by '#'.
+
+`read` / `read_one` / `shape` behave exactly like the reference (duplicates dropped, unknown names
+dropped, rows returned in ascending row order, vectors as Python lists) but go through one np.memmap
+instead of an open+seek+fromfile per row.  `rows` / `read_matrix` / `read_csr` are the B200 ingest path:
+they return index arrays (or the matrix) so that the whole gather + mean-pool + normalise happens in ONE
+device pass (frx_finalize_posts with row_ptr / row_idx) instead of 94 posts/s of Python lists.
+"""
+import os
+
+import numpy as np
+
+
+class ImageBigFile:
+    def __init__(self, datadir):
+        with open(os.path.join(datadir, 'shape.txt')) as f:
+            self.nr_of_images, self.ndims = map(int, f.readline().split())
+        with open(os.path.join(datadir, "id.txt"), encoding='utf8') as f:
+            self.names = f.readline().strip().split('#')
+        assert (len(self.names) == self.nr_of_images)
+        self.name2index = dict(zip(self.names, range(self.nr_of_images)))
+        self.binary_file = os.path.join(datadir, "feature.bin")
+        self._mm = None
+        print("[%s] %dx%d instances loaded from %s" % (self.__class__.__name__, self.nr_of_images, self.ndims, datadir))
+
+    # ---- bulk path ---------------------------------------------------------------------------
+    @property
+    def matrix(self):
+        """The whole feature matrix as a read-only np.memmap [N, ndims] float32."""
+        if self._mm is None:
+            self._mm = np.memmap(self.binary_file, dtype=np.float32, mode='r',
+                                 shape=(self.nr_of_images, self.ndims))
+        return self._mm
+
+    def rows(self, requested, isname=True):
+        """Sorted unique row indices of the requested names (unknown names dropped) / indices."""
+        requested = set(requested)
+        if isname:
+            idx = [self.name2index[x] for x in requested if x in self.name2index]
+        else:
+            if len(requested):
+                assert (min(requested) >= 0)
+                assert (max(requested) < len(self.names))
+            idx = list(requested)
+        return np.array(sorted(idx), dtype=np.int64)
+
+    def read_matrix(self, requested, isname=True):
+        idx = self.rows(requested, isname)
+        return [self.names[i] for i in idx], np.ascontiguousarray(self.matrix[idx])
+
+    def read_csr(self, frame_names_per_post):
+        """[[frame names of post 0], [post 1], ...] -> (row_idx int32 [total], row_ptr int64 [NP+1]):
+        post p owns rows row_idx[row_ptr[p]:row_ptr[p+1]] in the order given (the reference averages every
+        frame of a post, util/data_provider.py:40).  Feed both, with `matrix` on the device, to
+        fancyrec_b200.ops.finalize_posts(row_ptr=..., row_idx=...)."""
+        counts = np.fromiter((len(f) for f in frame_names_per_post), dtype=np.int64, count=len(frame_names_per_post))
+        row_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        row_idx = np.fromiter((self.name2index[n] for frames in frame_names_per_post for n in frames),
+                              dtype=np.int32, count=int(row_ptr[-1]))
+        return row_idx, row_ptr
+
+    # ---- reference API -----------------------------------------------------------------------
+    def read(self, requested, isname=True):
+        idx = self.rows(requested, isname)
+        if len(idx) == 0:
+            return [], []
+        block = np.asarray(self.matrix[idx], dtype=np.float32)
+        return [self.names[i] for i in idx], [row.tolist() for row in block]
+
+    def read_one(self, name):
+        renamed, vectors = self.read([name])
+        return vectors[0]
+
+    def shape(self):
+        return [self.nr_of_images, self.ndims]
