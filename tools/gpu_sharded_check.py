@@ -1,0 +1,36 @@
+"""torchrun --nproc-per-node N tools/gpu_sharded_check.py : N-rank NCCL sharded evaluation == single-GPU evaluation."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+from fancyrec_b200 import ops, ranking, sharded
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+nb, n, d, k = 300, 200003, 256, 100
+g = torch.Generator(device="cpu").manual_seed(5)
+brand = torch.randn(nb, d, generator=g)
+posts = torch.randn(n, d, generator=g)
+posts[::7] = posts[::7].round()          # some exact ties
+labels = (torch.randperm(n, generator=g) % (nb + 40))   # some labels out of brand range, none for a few brands
+labels[labels >= nb] = nb + 5
+lo, hi = sharded.shard_bounds(n, world, rank)
+a = ranking.to_operand(brand.to(dev))
+b_local = ranking.to_operand(posts[lo:hi].to(dev))
+lab_local = labels[lo:hi].to(dev, torch.int32)
+st = sharded.sharded_rank_statistics(a, b_local, lab_local, d, k, n)
+hs = ranking.host_statistics(st, n, want_auc=False)
+res = ranking.aggregate(hs, n, want_auc=False)
+if rank == 0:
+    b_full = ranking.to_operand(posts.to(dev))
+    ref = ranking.device_rank_statistics(a, b_full, labels.to(dev, torch.int32), d, k=k, want_auc=False)
+    hr = ranking.host_statistics(ref, n, want_auc=False)
+    rres = ranking.aggregate(hr, n, want_auc=False)
+    ok = (torch.equal(st["topk_index"], ref["topk_index"]) and torch.equal(st["topk_scores"], ref["topk_scores"])
+          and np.array_equal(hs["first_rank"], hr["first_rank"]) and np.array_equal(hs["hits"], hr["hits"])
+          and np.array_equal(hs["n_pos"], hr["n_pos"]) and tuple(map(float, res[:2] + res[3:])) == tuple(map(float, rres[:2] + rres[3:])))
+    print("sharded(%d ranks) == single GPU: %s ; result %s" % (world, ok, [float(x) for x in res]))
+    assert ok
+dist.barrier()
+dist.destroy_process_group()
