@@ -183,6 +183,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("FRX_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         torch.distributed.init_process_group("nccl", device_id=dev)
     cfg = dict(CFG)
     nb, n_local = args.brands, args.posts_per_gpu
