@@ -303,6 +303,61 @@ __global__ void __launch_bounds__(256) finalize_stream_kernel(FinalizeParams P) 
   }
 }
 
+// Block-per-row variant for long un-pooled rows (1024 < D <= 4096; the config-2 shape): 256 threads hold
+// the row in registers (VPT float4 each, 12-16 registers), ONE block reduction per row (double-buffered
+// scratch -> a single __syncthreads), reciprocal scaling.  ~40 registers/thread -> 8 blocks = 64 warps per
+// SM keep the HBM pipe full while other blocks are in their reduction / store phase.
+template <int VPT>
+__global__ void __launch_bounds__(256) finalize_block_kernel(FinalizeParams P) {
+  __shared__ float red[2][2][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int d = P.dv + P.dt;
+  const bool vn = (P.flags & FRX_VISUAL_NORM) != 0, tn = (P.flags & FRX_TEXT_NORM) != 0 && P.dt > 0;
+  const bool fn = (P.flags & FRX_FINAL_NORM) != 0;
+  int buf = 0;
+  for (int64_t p = blockIdx.x; p < P.n_posts; p += gridDim.x, buf ^= 1) {
+    float4 x[VPT];
+    float ssv = 0.f, sst = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = (i * 256 + tid) * 4;
+      x[i] = c < d ? ld_row_f4(P, p, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = (i * 256 + tid) * 4;
+      const float q = x[i].x * x[i].x + x[i].y * x[i].y + x[i].z * x[i].z + x[i].w * x[i].w;
+      if (c < P.dv) ssv += q; else sst += q;
+    }
+    ssv = warp_sum(ssv);
+    sst = warp_sum(sst);
+    if (lane == 0) { red[buf][0][warp] = ssv; red[buf][1][warp] = sst; }
+    __syncthreads();
+    float tv = 0.f, tt = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { tv += red[buf][0][w]; tt += red[buf][1][w]; }
+    const float iv = vn ? 1.0f / sqrtf(tv) : 1.f, it = tn ? 1.0f / sqrtf(tt) : 1.f;
+    const float total = (vn || tn) ? tv * iv * iv + tt * it * it : tv + tt;
+    const float inv_nrm = fn ? 1.0f / sqrtf(total) : 1.f;
+    const float sv = iv * inv_nrm, st = it * inv_nrm;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = (i * 256 + tid) * 4;
+      if (c < d) {
+        const float sc = c < P.dv ? sv : st;
+        float4 a = x[i];
+        a.x *= sc; a.y *= sc; a.z *= sc; a.w *= sc;
+        if (P.out_f32) *reinterpret_cast<float4*>(P.out_f32 + p * d + c) = a;
+        if (P.out_bf16) Vec<4>::st_bf16(P.out_bf16 + p * P.ld_bf16 + c, a);
+      }
+    }
+    if (P.out_bf16) {
+      for (int64_t c = d + tid * 4; c < P.ld_bf16; c += 1024)
+        *reinterpret_cast<uint2*>(P.out_bf16 + p * P.ld_bf16 + c) = make_uint2(0u, 0u);
+    }
+  }
+}
+
 template <int NV>
 static void launch_finalize_warp(const FinalizeParams& P, cudaStream_t st) {
   const int64_t warps_needed = P.n_posts;
@@ -398,7 +453,14 @@ int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_
                    aligned16(out_bf16);
   int grid = (int)(n_posts < (int64_t)num_sms() * 8 ? n_posts : (int64_t)num_sms() * 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (vec && row_ptr == nullptr && d > 1024 && ld_bf16 % 4 == 0) {
+  if (vec && row_ptr == nullptr && d > 1024 && d <= 4096 && ld_bf16 % 4 == 0) {
+    int64_t blocks = n_posts;
+    const int64_t max_blocks = (int64_t)num_sms() * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (d <= 2048) finalize_block_kernel<2><<<(int)blocks, 256, 0, st>>>(P);
+    else if (d <= 3072) finalize_block_kernel<3><<<(int)blocks, 256, 0, st>>>(P);
+    else finalize_block_kernel<4><<<(int)blocks, 256, 0, st>>>(P);
+  } else if (vec && row_ptr == nullptr && d > 4096 && ld_bf16 % 4 == 0) {
     int64_t blocks = (n_posts + 7) / 8;
     const int64_t max_blocks = (int64_t)num_sms() * 8;
     if (blocks > max_blocks) blocks = max_blocks;

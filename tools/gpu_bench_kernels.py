@@ -42,6 +42,28 @@ del frames
 a = ranking.to_operand(ops.brand_embed(w, e, nb=nb))
 b = ops.finalize_posts(visual, text, visual_norm=True, text_norm=True, final_norm=True)[1]
 lab = (torch.randperm(n, generator=g, device=dev) % nb).to(torch.int32)
+import bench as _bench
+def sustained(name, fn, flops, secs=2.0):
+    fn(); torch.cuda.synchronize()
+    smp = _bench.ClockSampler(0); smp.start()
+    t0 = time.time(); n = 0
+    b, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b.record()
+    while time.time() - t0 < secs:
+        for _ in range(10): fn()
+        n += 10
+        torch.cuda.synchronize()
+    en.record(); torch.cuda.synchronize()
+    ms = b.elapsed_time(en) / n
+    c = smp.stop()
+    print("%-42s %.3f ms  %.0f TFLOP/s  sm_mhz(median)=%s reasons=%s" % (name, ms, flops / ms / 1e9, c["sm_mhz"], c["reasons"]))
+F = 2 * nb * n * 3072
+thr_s = torch.zeros(nb, device=dev); thr_i = torch.zeros(nb, dtype=torch.int32, device=dev)
+sustained("sustained score_count", lambda: ops.score_count(a, b, thr_s, thr_i, d=3072), F)
+sustained("sustained score_topk k=100 labels", lambda: ops.score_topk(a, b, 100, d=3072, labels=lab), F)
+sustained("sustained score_topk k=100 no labels", lambda: ops.score_topk(a, b, 100, d=3072), F)
+am = a.float() ; bm = b[:, :3072]
+sustained("sustained torch.matmul bf16 (cuBLAS) 1000x1Mx3072", lambda: torch.matmul(a, b.t()), F)
 for k in (64, 100, 1000):
     t = timeit(lambda: ops.score_topk(a, b, k, d=3072, labels=lab))
     print("score_topk k=%4d (kernel+merge):         %.3f ms  %.0f TFLOP/s" % (k, t, 2 * nb * n * 3072 / t / 1e9))
