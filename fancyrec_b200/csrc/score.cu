@@ -37,6 +37,7 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = (EPI_WARP0 + NUM_EPI_WARPS) * 32;   // 384
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_MERGE_KEYS = 16384;
+constexpr int64_t kSampleMinPosts = 262144;   // below this the warm-up is too short to be worth a sample pass
 
 enum Mode { MODE_TOPK = 0, MODE_DENSE = 1, MODE_COUNT = 2 };
 
@@ -326,9 +327,12 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 const float s = __uint_as_float(v[i]);
-                if (i < nvalid && s >= thr) {
-                  rowbuf[cnt] = make_key(s, gbase + i);
-                  ++cnt;
+                const bool hit = i < nvalid && s >= thr;
+                if (__any_sync(0xffffffffu, hit)) {          // warp-uniform: most columns have no hit in any row
+                  if (hit) {
+                    rowbuf[cnt] = make_key(s, gbase + i);
+                    ++cnt;
+                  }
                 }
               }
               // keep room for the next 32-column chunk
@@ -542,6 +546,15 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long
   }
 }
 
+// row_thr[b] = ordered(k-th best score of the sample pass) -- a valid lower bound of the row's global k-th best
+// because the sample is a subset of the posts.  Rows whose sample list is short keep 0 (= no threshold).
+__global__ void seed_threshold_kernel(const float* __restrict__ topk_scores, int nb, int k, uint32_t* __restrict__ row_thr) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const float s = topk_scores[(size_t)b * k + (k - 1)];
+  row_thr[b] = (s == s && s > -INFINITY) ? score_to_ordered(s) : 0u;
+}
+
 // Merge g lists [g, nb, k_in] of (score, index) into [nb, k_out] (multi-GPU exchange step).
 __global__ void __launch_bounds__(256) merge_lists_kernel(const float* __restrict__ in_s, const int32_t* __restrict__ in_i,
                                                           int g, int nb, int k_in, float* __restrict__ out_s,
@@ -656,9 +669,40 @@ struct Probe {
 };
 static Probe g_probe;
 
+// Workspace layout of frx_score_topk: [part_cnt | row_thr | part_keys], each region sized for the larger of
+// the main pass and the sample pass (which reuses them).
+struct TopkLayout {
+  Plan main, sample;
+  bool has_sample;
+  int64_t n_s, stride;
+  size_t cnt_bytes, thr_bytes, keys_bytes;
+  size_t total() const { return cnt_bytes + thr_bytes + keys_bytes + 256; }
+};
+
+static TopkLayout make_topk_layout(int nb, int64_t n_posts, int k) {
+  TopkLayout L{};
+  L.main = make_plan(nb, n_posts, k, MODE_TOPK);
+  L.cnt_bytes = L.main.cnt_bytes;
+  L.keys_bytes = L.main.keys_bytes;
+  L.thr_bytes = L.main.thr_bytes;
+  L.has_sample = n_posts >= kSampleMinPosts;
+  if (L.has_sample) {
+    int64_t n_s = n_posts / 64;
+    n_s = n_s < 8192 ? 8192 : (n_s > 32768 ? 32768 : n_s);
+    if (n_s < 4 * (int64_t)k) n_s = 4 * (int64_t)k;
+    n_s = (n_s + BN - 1) / BN * BN;
+    L.n_s = n_s;
+    L.stride = n_posts / n_s;
+    L.sample = make_plan(nb, n_s, k, MODE_TOPK);
+    if (L.sample.cnt_bytes > L.cnt_bytes) L.cnt_bytes = L.sample.cnt_bytes;
+    if (L.sample.keys_bytes > L.keys_bytes) L.keys_bytes = L.sample.keys_bytes;
+  }
+  return L;
+}
+
 template <int MODE>
 static int launch_score(const uint16_t* a, int64_t ld_a, const uint16_t* b, int64_t ld_b, int nb, int64_t n_posts, int d,
-                        const Plan& plan, ScoreParams& P, cudaStream_t st) {
+                        const Plan& plan, ScoreParams& P, cudaStream_t st, bool allow_probe = true) {
   CUtensorMap ma, mb;
   int rc = make_operand_map(&ma, a, nb, d, ld_a, BM);
   if (rc) return rc;
@@ -671,7 +715,7 @@ static int launch_score(const uint16_t* a, int64_t ld_a, const uint16_t* b, int6
   P.num_n_tiles = plan.num_n_tiles;
   P.splits = plan.splits;
   FRX_CUDA(cudaFuncSetAttribute(score_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  const bool probe = g_probe.on && g_probe.n < 4096;
+  const bool probe = allow_probe && g_probe.on && g_probe.n < 4096;
   const int slot = g_probe.n;
   if (probe) {
     if (!g_probe.made[slot]) {
@@ -709,8 +753,7 @@ extern "C" {
 size_t frx_score_topk_workspace_bytes(int nb, int64_t n_posts, int d, int k) {
   (void)d;
   if (nb <= 0 || n_posts <= 0 || k <= 0 || k > 1024) return 0;
-  frx::Plan p = frx::make_plan(nb, n_posts, k, frx::MODE_TOPK);
-  return p.keys_bytes + p.cnt_bytes + p.thr_bytes + 256;
+  return frx::make_topk_layout(nb, n_posts, k).total();
 }
 
 int frx_score_topk(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* post_bf16, int64_t ld_b, int nb,
@@ -725,8 +768,9 @@ int frx_score_topk(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* pos
   FRX_CHECK_ARG((labels == nullptr) == (pos_score == nullptr), "frx_score_topk: labels and pos_score go together");
   FRX_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "frx_score_topk: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  Plan plan = make_plan(nb, n_posts, k, MODE_TOPK);
-  const size_t need = plan.keys_bytes + plan.cnt_bytes + plan.thr_bytes + 256;
+  const TopkLayout L = make_topk_layout(nb, n_posts, k);
+  const Plan& plan = L.main;
+  const size_t need = L.total();
   if (workspace == nullptr || workspace_bytes < need) {
     set_error("frx_score_topk: workspace %zu bytes, need %zu", workspace_bytes, need);
     return FRX_E_WORKSPACE;
@@ -737,24 +781,50 @@ int frx_score_topk(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* pos
   P.cap = plan.cap;
   P.keep_limit = plan.keep_limit;
   P.part_cnt = reinterpret_cast<int*>(workspace);
-  P.row_thr = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + plan.cnt_bytes);
-  P.part_keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(workspace) + plan.cnt_bytes + plan.thr_bytes);
-  FRX_CUDA(cudaMemsetAsync(P.row_thr, 0, plan.thr_bytes, st));     // ordered 0 = below every score
+  P.row_thr = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + L.cnt_bytes);
+  P.part_keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(workspace) + L.cnt_bytes + L.thr_bytes);
+  FRX_CUDA(cudaMemsetAsync(P.row_thr, 0, L.thr_bytes, st));        // ordered 0 = below every score
   P.labels = labels;
   P.pos_score = pos_score;
   if (pos_score) FRX_CUDA(cudaMemsetAsync(pos_score, 0xFF, (size_t)n_posts * sizeof(float), st));   // NaN
+  auto run_merge = [&](const Plan& pl) -> int {
+    const int total_max = pl.splits * 2 * k;
+    int np2 = 2;
+    while (np2 < 2 * k) np2 <<= 1;                                 // sort buffer when nothing needs selecting
+    const size_t mkeys = (size_t)(total_max + k) > (size_t)np2 ? (size_t)(total_max + k) : (size_t)np2;
+    const size_t msmem = mkeys * sizeof(unsigned long long);
+    if (msmem > 48 * 1024)
+      FRX_CUDA(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    merge_partials_kernel<<<nb, 256, msmem, st>>>(P.part_keys, P.part_cnt, P.row_thr, pl.num_m_tiles, pl.splits, pl.cap, k,
+                                                  topk_scores, topk_index);
+    FRX_LAUNCH_CHECK();
+    return FRX_OK;
+  };
+  // ---- sample pass: seed the per-row thresholds ------------------------------------------------
+  // The fused kernel is first run on a strided 1/64..1/16 sample of the posts (a TMA view with a larger
+  // row pitch: no data is moved).  The k-th best score of the sample is a valid lower bound of the
+  // global k-th best, so the main pass starts with a pass rate of ~k/n_sample instead of warming every
+  // candidate list up from -inf; candidates appended per row drop by an order of magnitude.
+  if (L.has_sample) {
+    const int64_t n_s = L.n_s, stride = L.stride;
+    const Plan& ps = L.sample;
+    ScoreParams S = P;
+    S.labels = nullptr;
+    S.pos_score = nullptr;
+    S.index_base = 0;
+    S.cap = ps.cap;
+    S.keep_limit = ps.keep_limit;
+    rc = launch_score<MODE_TOPK>(brand_bf16, ld_a, post_bf16, ld_b * stride, nb, n_s, d, ps, S, st, false);
+    if (rc) return rc;
+    rc = run_merge(ps);
+    if (rc) return rc;
+    seed_threshold_kernel<<<(nb + 255) / 256, 256, 0, st>>>(topk_scores, nb, k, P.row_thr);
+    FRX_LAUNCH_CHECK();
+  }
   rc = launch_score<MODE_TOPK>(brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, plan, P, st);
   if (rc) return rc;
-  const int total_max = plan.splits * 2 * k;
-  int np2 = 2;
-  while (np2 < 2 * k) np2 <<= 1;                                 // sort buffer when nothing needs selecting
-  const size_t mkeys = (size_t)(total_max + k) > (size_t)np2 ? (size_t)(total_max + k) : (size_t)np2;
-  const size_t msmem = mkeys * sizeof(unsigned long long);
-  if (msmem > 48 * 1024)
-    FRX_CUDA(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-  merge_partials_kernel<<<nb, 256, msmem, st>>>(P.part_keys, P.part_cnt, P.row_thr, plan.num_m_tiles, plan.splits, plan.cap, k,
-                                                topk_scores, topk_index);
-  FRX_LAUNCH_CHECK();
+  rc = run_merge(plan);
+  if (rc) return rc;
   if (dense_out) return frx_score_dense(brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, dense_out, ld_dense, stream);
   return FRX_OK;
 }

@@ -61,6 +61,26 @@ def test_lattice_scores_bit_exact_vs_fp32_reference(golden_dir, name):
     assert np.array_equal(ps, g["scores"][lab, np.arange(len(lab))])
 
 
+@pytest.mark.parametrize("kind,k", [("gauss", 100), ("lattice", 64), ("gauss", 1000)])
+def test_sample_seeded_thresholds_large_np(kind, k):
+    """n_posts >= 262144 takes the sample pass (strided TMA view) that seeds the per-row thresholds;
+    the result must still be the exact top-k."""
+    nb, npost, d = 40, 300000, 64
+    rs = np.random.RandomState(k)
+    if kind == "lattice":
+        brand = synth.lattice(11, nb, d, nnz=16)
+        posts = synth.lattice(12, 3000, d, nnz=16)[rs.randint(0, 3000, npost)]    # massive exact ties
+    else:
+        brand = rs.standard_normal((nb, d)).astype(np.float32)
+        posts = rs.standard_normal((npost, d)).astype(np.float32)
+    lab = synth.labels(13, npost, nb)
+    res, dense, _, _ = _dense_and_topk(brand, posts, k, labels=lab, index_base=7)
+    want = oref.topk_indices(dense, k)
+    assert np.array_equal(res["index"].cpu().numpy(), want + 7)
+    assert np.array_equal(res["scores"].cpu().numpy(), np.take_along_axis(dense, want, 1))
+    assert np.array_equal(res["pos_score"].cpu().numpy(), dense[lab, np.arange(npost)])
+
+
 def test_heavy_ties_and_index_base():
     """Quantised scores (few distinct values) -> the tie-break carries the whole ranking."""
     rs = np.random.RandomState(3)
