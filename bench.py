@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -70,9 +70,10 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples that arrived in [t0, t1] (perf_counter); all samples when none did."""
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
@@ -82,7 +83,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        inside = [l for (t, l) in self.lines if t0 is not None and t0 <= t <= t1]
+        window = "timed region"
+        if not inside:
+            inside, window = [l for (_, l) in self.lines], "warm-up + timed region (timed region shorter than the sampling period)"
+        for line in inside:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -94,7 +99,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(smax) if smax else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), window=window)
 
 
 def peaks():
@@ -156,8 +161,9 @@ class Evaluator:
         st = self.sharded.sharded_rank_statistics(brand_op, post_op, labels, self.d, self.cfg["k"], self.n_total,
                                                   workspace=self.workspace)
         self.workspace = st["workspace"]
-        # score kernel + merge_partials + label_stats + decode_best + rank_from_topk (+ merge_lists, + count)
-        self.launches = 3 + 5 + (1 if self.world > 1 else 0) + (1 if bool(st["before_first_valid"].any()) else 0)
+        # brand_embed, 2 x finalize | sample pass: score + merge + seed | main: score + merge | label_stats,
+        # decode_best, rank_from_topk (+ merge_lists when sharded, + count pass when a first positive is deep)
+        self.launches = 3 + 3 + 2 + 3 + (1 if self.world > 1 else 0) + (1 if st["count_pass"] else 0)
         stats = self.ranking.host_statistics(st, self.n_total, want_auc=False)          # D2H of NB-length arrays
         return self.ranking.aggregate(stats, self.n_total, want_auc=False), st
 
@@ -192,29 +198,31 @@ def run_ours(args):
     ev = Evaluator(dev, world, rank, nb, n_local, cfg)
     pk = peaks()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                  # nvidia-smi needs ~100 ms to start reporting: start before warm-up
     for _ in range(max(args.warmup, 3)):
         result, st = ev.step(w, e, labels, visual, text)
     barrier_sync(world)
 
     # ---- timed region: K steps, device resident inputs (12.3 GB of fp32 inputs per step >> 126 MB L2)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev.lib.frx_probe_enable(1)
     beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier_sync(world)
     profile_range = bool(os.environ.get("FRX_PROFILE_RANGE"))   # ncu --profile-from-start off
     if profile_range:
         torch.cuda.profiler.start()
+    t_start = time.perf_counter()
     beg.record()
     for _ in range(args.steps):
         result, st = ev.step(w, e, labels, visual, text)
     end.record()
     barrier_sync(world)
+    t_end = time.perf_counter()
     if profile_range:
         torch.cuda.profiler.stop()
     ms_total = max_over_ranks(beg.elapsed_time(end), dev, world)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_start, t_end) if rank == 0 else None
     buf = (torch.zeros(4096, dtype=torch.float32)).numpy()
     n_probe = ev.lib.frx_probe_read(buf.ctypes.data, 4096)
     ev.lib.frx_probe_enable(0)

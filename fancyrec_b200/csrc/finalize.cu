@@ -427,6 +427,78 @@ __global__ void __launch_bounds__(256) brand_embed_kernel(const float* __restric
     }
 }
 
+// Faster variant when A % 8 == 0 and D % 4 == 0 (the usual 2000 x {1024, 2048, 3072}): 128x128x8 tiles,
+// 8x8 outputs per thread, 128-bit shared-memory reads, register-staged double buffering.
+constexpr int kFM = 128, kFN = 128, kFK = 8;
+
+__global__ void __launch_bounds__(256) brand_embed_kernel_128(const float* __restrict__ w, const float* __restrict__ e,
+                                                               const int64_t* __restrict__ ids, int nb, int a, int d,
+                                                               float* __restrict__ out) {
+  __shared__ __align__(16) float sw[2][kFK][kFM];   // W tile, k-major
+  __shared__ __align__(16) float se[2][kFK][kFN];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * kFM, n0 = blockIdx.x * kFN;
+  const int ty = tid >> 4, tx = tid & 15;
+  // global -> register staging: W: row (tid >> 1), k offset (tid & 1) * 4 ; E: k (tid >> 5), col (tid & 31) * 4
+  const int wm = tid >> 1, wk = (tid & 1) * 4;
+  const int ek = tid >> 5, en = (tid & 31) * 4;
+  const bool w_ok = m0 + wm < nb;
+  const int64_t wrow = w_ok ? (ids ? ids[m0 + wm] : (int64_t)(m0 + wm)) : 0;
+  const float* wp = w + wrow * a + wk;
+  const bool e_ok = n0 + en < d;
+  const float* ep = e + (int64_t)ek * d + n0 + en;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float4 rw = w_ok ? __ldg(reinterpret_cast<const float4*>(wp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 re = e_ok ? __ldg(reinterpret_cast<const float4*>(ep)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  sw[0][wk + 0][wm] = rw.x; sw[0][wk + 1][wm] = rw.y; sw[0][wk + 2][wm] = rw.z; sw[0][wk + 3][wm] = rw.w;
+  *reinterpret_cast<float4*>(&se[0][ek][en]) = re;
+  __syncthreads();
+  const int nk = a / kFK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) {
+      rw = w_ok ? __ldg(reinterpret_cast<const float4*>(wp + (kt + 1) * kFK)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      re = e_ok ? __ldg(reinterpret_cast<const float4*>(ep + (int64_t)(kt + 1) * kFK * d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < kFK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&sw[cur][k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sw[cur][k][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&se[cur][k][tx * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&se[cur][k][tx * 8 + 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      const int nxt = cur ^ 1;
+      sw[nxt][wk + 0][wm] = rw.x; sw[nxt][wk + 1][wm] = rw.y; sw[nxt][wk + 2][wm] = rw.z; sw[nxt][wk + 3][wm] = rw.w;
+      *reinterpret_cast<float4*>(&se[nxt][ek][en]) = re;
+    }
+    __syncthreads();
+  }
+  const float fa = (float)a;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
+    if (m >= nb) continue;
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) {
+      const int n = n0 + tx * 8 + j;
+      if (n < d)
+        *reinterpret_cast<float4*>(out + (int64_t)m * d + n) =
+            make_float4(acc[i][j] / fa, acc[i][j + 1] / fa, acc[i][j + 2] / fa, acc[i][j + 3] / fa);
+    }
+  }
+}
+
 }  // namespace frx
 
 extern "C" {
@@ -488,8 +560,15 @@ int frx_brand_embed(const float* w, int64_t w_rows, const float* e, const int64_
   FRX_CHECK_ARG(nb >= 0 && a > 0 && d > 0, "frx_brand_embed: bad sizes nb=%d a=%d d=%d", nb, a, d);
   FRX_CHECK_ARG(brand_ids != nullptr || nb <= w_rows, "frx_brand_embed: nb=%d exceeds table rows %lld", nb, (long long)w_rows);
   if (nb == 0) return FRX_OK;
-  dim3 grid((d + kBN - 1) / kBN, (nb + kBM - 1) / kBM);
-  brand_embed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, e, brand_ids, nb, a, d, out_f32);
+  const bool aligned = (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(e) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0;
+  if (a % kFK == 0 && d % 4 == 0 && aligned) {
+    dim3 grid((d + kFN - 1) / kFN, (nb + kFM - 1) / kFM);
+    brand_embed_kernel_128<<<grid, 256, 0, (cudaStream_t)stream>>>(w, e, brand_ids, nb, a, d, out_f32);
+  } else {
+    dim3 grid((d + kBN - 1) / kBN, (nb + kBM - 1) / kBM);
+    brand_embed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, e, brand_ids, nb, a, d, out_f32);
+  }
   FRX_LAUNCH_CHECK();
   return FRX_OK;
 }

@@ -68,19 +68,23 @@ def device_rank_statistics(brand_bf16, post_bf16, labels_i32, d, k=MIN_TOPK, wan
 
 
 def host_statistics(dev_stats, n_posts, want_auc=True):
-    """Device statistics -> the integer per-brand arrays the metrics are functions of (NumPy, host)."""
-    n_pos = dev_stats["n_pos"].cpu().numpy().astype(np.int64)
-    first_in_list = dev_stats["first_in_list"].cpu().numpy().astype(np.int64)
-    before = dev_stats["before_first"].cpu().numpy().astype(np.int64)
-    valid = dev_stats["before_first_valid"].cpu().numpy()
+    """Device statistics -> the integer per-brand arrays the metrics are functions of (NumPy, host).
+    Everything is packed into one int64 [rows, NB] tensor so that the device->host read is ONE copy."""
+    rows = [dev_stats["n_pos"].to(torch.int64), dev_stats["first_in_list"].to(torch.int64),
+            dev_stats["before_first"].to(torch.int64), dev_stats["before_first_valid"].to(torch.int64),
+            dev_stats["hit_mask"].to(torch.int64)]
+    if want_auc:
+        rows.append(dev_stats["auc_num"].to(torch.int64))
+    packed = torch.stack(rows).cpu().numpy()
+    n_pos, first_in_list, before, valid, mask = packed[0], packed[1], packed[2], packed[3] != 0, packed[4]
     first_rank = np.where(valid, before, first_in_list)
     first_rank = np.where(n_pos > 0, first_rank, -1)
-    mask = dev_stats["hit_mask"].cpu().numpy().view(np.uint64)
+    mask = np.ascontiguousarray(mask).view(np.uint64)
     depth = min(HIT_DEPTH, n_posts)
     hits = ((mask[:, None] >> np.arange(depth, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(np.uint8)
-    st = dict(n_pos=n_pos, first_rank=first_rank, hits=hits)
+    st = dict(n_pos=n_pos.copy(), first_rank=first_rank, hits=hits)
     if want_auc:
-        st["auc_num"] = dev_stats["auc_num"].cpu().numpy().astype(np.int64)
+        st["auc_num"] = packed[5].copy()
     return st
 
 

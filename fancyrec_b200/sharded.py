@@ -104,10 +104,11 @@ def sharded_rank_statistics(brand_op, post_op_local, labels_local, d, k, n_posts
     hit_mask, first_in_list = kernels.rank_from_topk(top_i, labels_all, 0)
     missing = (first_in_list < 0) & (n_pos > 0)
     before = torch.zeros(nb, dtype=torch.int64, device=post_op_local.device)
-    if bool(missing.any().item()):                 # same decision on every rank (inputs are global)
+    need_count = bool(missing.any().item())        # same decision on every rank (inputs are global)
+    if need_count:
         thr_index = torch.where(missing, best_i, torch.full_like(best_i, -1))
         kernels.score_count(brand_op, post_op_local, best_s, thr_index, d=d, index_base=lo, out=before)
         all_sum(before, group)
     return dict(topk_scores=top_s, topk_index=top_i, n_pos=n_pos, best_score=best_s, best_index=best_i,
                 hit_mask=hit_mask, first_in_list=first_in_list, before_first=before,
-                before_first_valid=missing, workspace=res.get("workspace"))
+                before_first_valid=missing, workspace=res.get("workspace"), count_pass=need_count)
