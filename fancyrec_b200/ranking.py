@@ -88,23 +88,36 @@ def host_statistics(dev_stats, n_posts, want_auc=True):
     return st
 
 
+_IDEAL_CACHE = {}
+
+
+def _ideal_table(depth):
+    """ideal DCG for m = 0..depth ones followed by zeros, each computed with the reference's expression
+    (util/ndcg.py:37-42 on sorted(r, reverse=True)); cached, it only depends on `depth`."""
+    tab = _IDEAL_CACHE.get(depth)
+    if tab is None:
+        disc = np.log2(np.arange(2, depth + 1)) if depth > 1 else None
+        tab = np.zeros(depth + 1, dtype=np.float64)
+        for m in range(1, depth + 1):
+            ideal = np.zeros(depth, dtype=np.float64)
+            ideal[:m] = 1.0
+            tab[m] = ideal[0] + (np.sum(ideal[1:] / disc) if depth > 1 else 0.0)
+        _IDEAL_CACHE[depth] = (tab, disc)
+        tab = _IDEAL_CACHE[depth]
+    return tab
+
+
 def _ndcg_rows(hits, n_pos, k, n_posts):
     """ndcg_at_k (util/ndcg.py:48-78) for every row of a 0/1 `hits` matrix at once.  Row reductions run
     over the contiguous last axis, so NumPy applies to each row the same pairwise summation it applies
     to the reference's 1-D np.sum -- results are bit-identical (tests/test_abi.py checks this)."""
     depth = min(k, n_posts, hits.shape[1])
+    table, disc = _ideal_table(depth)
     r = np.ascontiguousarray(hits[:, :depth], dtype=np.float64)
     if depth > 1:
-        disc = np.log2(np.arange(2, depth + 1))
         dcg = r[:, 0] + np.sum(np.ascontiguousarray(r[:, 1:] / disc), axis=1)
     else:
         dcg = r[:, 0].copy()
-    # ideal DCG depends only on min(n_pos, depth): a table of depth + 1 scalars, computed like the reference
-    table = np.zeros(depth + 1, dtype=np.float64)
-    for m in range(1, depth + 1):
-        ideal = np.zeros(depth, dtype=np.float64)
-        ideal[:m] = 1.0
-        table[m] = ideal[0] + (np.sum(ideal[1:] / np.log2(np.arange(2, depth + 1))) if depth > 1 else 0.0)
     best = table[np.minimum(n_pos, depth)]
     out = np.zeros(len(n_pos), dtype=np.float64)
     nz = best != 0
