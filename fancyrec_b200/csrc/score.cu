@@ -793,7 +793,7 @@ int frx_score_topk(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* pos
     while (np2 < 2 * k) np2 <<= 1;                                 // sort buffer when nothing needs selecting
     const size_t mkeys = (size_t)(total_max + k) > (size_t)np2 ? (size_t)(total_max + k) : (size_t)np2;
     const size_t msmem = mkeys * sizeof(unsigned long long);
-    if (msmem > 48 * 1024)
+    if (msmem > 32 * 1024)   // static smem (~10 KB) counts against the 48 KB default too
       FRX_CUDA(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
     merge_partials_kernel<<<nb, 256, msmem, st>>>(P.part_keys, P.part_cnt, P.row_thr, pl.num_m_tiles, pl.splits, pl.cap, k,
                                                   topk_scores, topk_index);
@@ -884,7 +884,7 @@ int frx_topk_merge(const float* in_scores, const int32_t* in_index, int g, int n
   int np2 = 2;
   while (np2 < g * k_in) np2 <<= 1;
   const size_t msmem = (size_t)np2 * sizeof(unsigned long long);
-  if (msmem > 48 * 1024)
+  if (msmem > 32 * 1024)
     FRX_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
   merge_lists_kernel<<<nb, 256, msmem, (cudaStream_t)stream>>>(in_scores, in_index, g, nb, k_in, out_scores, out_index, k_out);
   FRX_LAUNCH_CHECK();

@@ -30,6 +30,7 @@ def _dense_and_topk(brand, posts, k, labels=None, index_base=0):
 @pytest.mark.parametrize("nb,npost,d,k", [
     (5, 257, 48, 10), (1, 37, 64, 64), (50, 10000, 1024, 64), (130, 3000, 200, 100),
     (300, 70001, 256, 100), (64, 5000, 3072, 1000), (129, 513, 72, 1), (1000, 20000, 128, 100),
+    (50, 10000, 320, 64),     # 80 candidate lists x 64: merge smem lands between 32 and 48 KB
 ])
 def test_topk_matches_oracle_on_our_scores(nb, npost, d, k):
     rs = np.random.RandomState(nb * 7 + npost)
