@@ -28,9 +28,12 @@
 namespace frx {
 using namespace sm100;
 
-constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 4;
-constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int BM = 128, BN = 256, STAGES = 4;
+// one k-block = one 128-byte swizzle row per operand row: 64 bf16 or 32 tf32 (fp32 storage); 4 MMAs per k-block
+// (K = 16 bf16 / 8 tf32 = 32 bytes each), so stage bytes and the per-MMA descriptor advance are the same in both modes
+constexpr int BK_BYTES = 128, MMAS_PER_KBLOCK = 4;
+constexpr int A_STAGE_BYTES = BM * BK_BYTES;   // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK_BYTES;   // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int EPI_WARP0 = 4;                 // warps 4..11: lane quarter = warp % 4, column half = (warp-4)/4
 constexpr int NUM_EPI_WARPS = 8;
@@ -134,12 +137,12 @@ __device__ __forceinline__ int warp_select(unsigned long long* buf, int n, int k
           atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
       }
     } else {
-      for (int base = 0; base < n; base += 256) {
-        unsigned long long kk[8];
+      for (int base = 0; base < n; base += 512) {          // 16 independent 8-byte loads in flight per lane
+        unsigned long long kk[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const int i = base + j * 32 + lane; kk[j] = i < n ? __ldcg(buf + i) : 0ull; }
+        for (int j = 0; j < 16; ++j) { const int i = base + j * 32 + lane; kk[j] = i < n ? __ldcg(buf + i) : 0ull; }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 16; ++j) {
           if (base + j * 32 + lane < n && (pass == 0 || (kk[j] >> (shift + 8)) == prefix))
             atomicAdd(&hist[(uint32_t)(kk[j] >> shift) & 255u], 1u);
         }
@@ -166,13 +169,18 @@ __device__ __forceinline__ int warp_select(unsigned long long* buf, int n, int k
       }
     }
   } else {
-    for (int base = 0; base < n; base += 32) {
-      const int i = base + lane;
-      const unsigned long long key = i < n ? __ldcg(buf + i) : 0ull;
-      const bool keep = i < n && key >= thr_key;
-      const uint32_t m = __ballot_sync(0xffffffffu, keep);
-      if (keep) buf[out + __popc(m & ((1u << lane) - 1u))] = key;   // out + rank <= i: never clobbers unread keys
-      out += __popc(m);
+    for (int base = 0; base < n; base += 512) {
+      unsigned long long kk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { const int i = base + j * 32 + lane; kk[j] = i < n ? __ldcg(buf + i) : 0ull; }
+      __syncwarp();                                        // every lane holds its 16 keys before anything is overwritten
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const bool keep = (base + j * 32 + lane < n) && kk[j] >= thr_key;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (keep) buf[out + __popc(m & ((1u << lane) - 1u))] = kk[j];   // out + rank <= source index: unread keys are safe
+        out += __popc(m);
+      }
       __syncwarp();
     }
   }
@@ -188,7 +196,7 @@ __device__ __forceinline__ int select_dispatch(int cap, unsigned long long* buf,
   return warp_select<0>(buf, n, k, keep_limit, exact, hist, thr_out);
 }
 
-template <int MODE>
+template <int MODE, bool TF32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const ScoreParams P) {
@@ -199,6 +207,7 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   SmemTail* tail = reinterpret_cast<SmemTail*>(smem + (size_t)STAGES * STAGE_BYTES);
   const uint32_t smem_a = base, smem_b = base + STAGES * A_STAGE_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int BK = TF32 ? 32 : 64;                      // operand elements per k-block
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
@@ -237,7 +246,7 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(BM, BN) : make_idesc_bf16(BM, BN);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -253,9 +262,10 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             const uint64_t da = make_sw128_kmajor_desc(smem_a + stage * A_STAGE_BYTES);
             const uint64_t db = make_sw128_kmajor_desc(smem_b + stage * B_STAGE_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
-              umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < MMAS_PER_KBLOCK; ++k) {
+              // advance 16 bf16 / 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
+              if (TF32) umma_tf32_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
             }
             umma_commit(smem_u32(&tail->empty[stage]));        // frees the smem slot when the MMAs retire
             if (kb == P.num_k_blocks - 1) umma_commit(smem_u32(&tail->tmem_full[as]));
@@ -609,14 +619,15 @@ static EncodeTiledFn get_encode_fn() {
 
 // [rows, d] bf16 row-major with leading dimension ld -> 2-D tensor map, box = 64 (K) x box_rows,
 // SWIZZLE_128B, out-of-bounds elements (row tails, K tail) read as zero.
-static int make_operand_map(CUtensorMap* map, const void* ptr, int64_t rows, int d, int64_t ld, int box_rows) {
+static int make_operand_map(CUtensorMap* map, const void* ptr, int64_t rows, int d, int64_t ld, int box_rows, bool tf32) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return FRX_E_DEVICE; }
   cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const int esize = tf32 ? 4 : 2;
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esize};
+  cuuint32_t box[2] = {(cuuint32_t)(BK_BYTES / esize), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return FRX_E_CUDA; }
@@ -689,6 +700,8 @@ static TopkLayout make_topk_layout(int nb, int64_t n_posts, int k) {
   if (L.has_sample) {
     int64_t n_s = n_posts / 64;
     n_s = n_s < 8192 ? 8192 : (n_s > 32768 ? 32768 : n_s);
+    if (n_s < 32 * (int64_t)k) n_s = 32 * (int64_t)k;          // keep the seeded pass rate k / n_s at <= 3 %
+    if (n_s > 32768) n_s = 32768;
     if (n_s < 4 * (int64_t)k) n_s = 4 * (int64_t)k;
     n_s = (n_s + BN - 1) / BN * BN;
     L.n_s = n_s;
@@ -700,21 +713,22 @@ static TopkLayout make_topk_layout(int nb, int64_t n_posts, int k) {
   return L;
 }
 
-template <int MODE>
-static int launch_score(const uint16_t* a, int64_t ld_a, const uint16_t* b, int64_t ld_b, int nb, int64_t n_posts, int d,
+template <int MODE, bool TF32>
+static int launch_score(const void* a, int64_t ld_a, const void* b, int64_t ld_b, int nb, int64_t n_posts, int d,
                         const Plan& plan, ScoreParams& P, cudaStream_t st, bool allow_probe = true) {
   CUtensorMap ma, mb;
-  int rc = make_operand_map(&ma, a, nb, d, ld_a, BM);
+  int rc = make_operand_map(&ma, a, nb, d, ld_a, BM, TF32);
   if (rc) return rc;
-  rc = make_operand_map(&mb, b, n_posts, d, ld_b, BN);
+  rc = make_operand_map(&mb, b, n_posts, d, ld_b, BN, TF32);
   if (rc) return rc;
   P.nb = nb;
   P.n_posts = n_posts;
+  constexpr int BK = TF32 ? 32 : 64;
   P.num_k_blocks = (d + BK - 1) / BK;
   P.num_m_tiles = plan.num_m_tiles;
   P.num_n_tiles = plan.num_n_tiles;
   P.splits = plan.splits;
-  FRX_CUDA(cudaFuncSetAttribute(score_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  FRX_CUDA(cudaFuncSetAttribute(score_kernel<MODE, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   const bool probe = allow_probe && g_probe.on && g_probe.n < 4096;
   const int slot = g_probe.n;
   if (probe) {
@@ -725,7 +739,7 @@ static int launch_score(const uint16_t* a, int64_t ld_a, const uint16_t* b, int6
     }
     FRX_CUDA(cudaEventRecord(g_probe.beg[slot], st));
   }
-  score_kernel<MODE><<<plan.grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
+  score_kernel<MODE, TF32><<<plan.grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
   FRX_LAUNCH_CHECK();
   if (probe) {
     FRX_CUDA(cudaEventRecord(g_probe.end[slot], st));
@@ -734,11 +748,13 @@ static int launch_score(const uint16_t* a, int64_t ld_a, const uint16_t* b, int6
   return FRX_OK;
 }
 
-static int check_operands(const char* fn, const uint16_t* a, int64_t ld_a, const uint16_t* b, int64_t ld_b, int nb,
-                          int64_t n_posts, int d, int64_t index_base) {
+static int check_operands(const char* fn, const void* a, int64_t ld_a, const void* b, int64_t ld_b, int nb,
+                          int64_t n_posts, int d, int64_t index_base, bool tf32) {
+  const int lda_mult = tf32 ? 4 : 8;      // row pitch must be a multiple of 16 bytes for TMA
   FRX_CHECK_ARG(a && b, "%s: NULL operand", fn);
   FRX_CHECK_ARG(nb > 0 && n_posts > 0 && d > 0, "%s: empty problem nb=%d n_posts=%lld d=%d", fn, nb, (long long)n_posts, d);
-  FRX_CHECK_ARG(ld_a >= d && ld_b >= d && ld_a % 8 == 0 && ld_b % 8 == 0, "%s: leading dimensions must be >= d and multiples of 8", fn);
+  FRX_CHECK_ARG(ld_a >= d && ld_b >= d && ld_a % lda_mult == 0 && ld_b % lda_mult == 0,
+                "%s: leading dimensions must be >= d and multiples of %d", fn, lda_mult);
   FRX_CHECK_ARG(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0, "%s: operands must be 16-byte aligned", fn);
   FRX_CHECK_ARG(index_base >= 0 && index_base + n_posts <= 2147483647LL, "%s: index_base + n_posts must fit int32", fn);
   int dev = 0;
@@ -746,22 +762,41 @@ static int check_operands(const char* fn, const uint16_t* a, int64_t ld_a, const
   return frx_device_check(dev);
 }
 
-}  // namespace frx
-
-extern "C" {
-
-size_t frx_score_topk_workspace_bytes(int nb, int64_t n_posts, int d, int k) {
-  (void)d;
-  if (nb <= 0 || n_posts <= 0 || k <= 0 || k > 1024) return 0;
-  return frx::make_topk_layout(nb, n_posts, k).total();
+template <bool TF32>
+static int score_dense_impl(const void* a, int64_t ld_a, const void* b, int64_t ld_b, int nb, int64_t n_posts, int d,
+                            float* dense_out, int64_t ld_dense, void* stream) {
+  int rc = check_operands("frx_score_dense", a, ld_a, b, ld_b, nb, n_posts, d, 0, TF32);
+  if (rc) return rc;
+  FRX_CHECK_ARG(dense_out && ld_dense >= n_posts, "frx_score_dense: bad output");
+  Plan plan = make_plan(nb, n_posts, 1, MODE_DENSE);
+  ScoreParams P{};
+  P.dense = dense_out;
+  P.ld_dense = ld_dense;
+  return launch_score<MODE_DENSE, TF32>(a, ld_a, b, ld_b, nb, n_posts, d, plan, P, (cudaStream_t)stream);
 }
 
-int frx_score_topk(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* post_bf16, int64_t ld_b, int nb,
-                   int64_t n_posts, int d, int k, const int32_t* labels, int64_t index_base, float* topk_scores,
-                   int32_t* topk_index, float* pos_score, float* dense_out, int64_t ld_dense, void* workspace,
-                   size_t workspace_bytes, void* stream) {
-  using namespace frx;
-  int rc = check_operands("frx_score_topk", brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, index_base);
+template <bool TF32>
+static int score_count_impl(const void* a, int64_t ld_a, const void* b, int64_t ld_b, int nb, int64_t n_posts, int d,
+                            int64_t index_base, const float* thr_score, const int32_t* thr_index,
+                            unsigned long long* count_out, void* stream) {
+  int rc = check_operands("frx_score_count", a, ld_a, b, ld_b, nb, n_posts, d, index_base, TF32);
+  if (rc) return rc;
+  FRX_CHECK_ARG(thr_score && thr_index && count_out, "frx_score_count: NULL pointer");
+  Plan plan = make_plan(nb, n_posts, 1, MODE_COUNT);
+  ScoreParams P{};
+  P.index_base = index_base;
+  P.thr_score = thr_score;
+  P.thr_index = thr_index;
+  P.count_out = count_out;
+  return launch_score<MODE_COUNT, TF32>(a, ld_a, b, ld_b, nb, n_posts, d, plan, P, (cudaStream_t)stream);
+}
+
+template <bool TF32>
+static int score_topk_impl(const void* a, int64_t ld_a, const void* b, int64_t ld_b, int nb, int64_t n_posts, int d, int k,
+                           const int32_t* labels, int64_t index_base, float* topk_scores, int32_t* topk_index,
+                           float* pos_score, float* dense_out, int64_t ld_dense, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  int rc = check_operands("frx_score_topk", a, ld_a, b, ld_b, nb, n_posts, d, index_base, TF32);
   if (rc) return rc;
   FRX_CHECK_ARG(k >= 1 && k <= 1024, "frx_score_topk: k=%d outside 1..1024", k);
   FRX_CHECK_ARG(topk_scores && topk_index, "frx_score_topk: NULL output");
@@ -801,10 +836,10 @@ int frx_score_topk(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* pos
     return FRX_OK;
   };
   // ---- sample pass: seed the per-row thresholds ------------------------------------------------
-  // The fused kernel is first run on a strided 1/64..1/16 sample of the posts (a TMA view with a larger
-  // row pitch: no data is moved).  The k-th best score of the sample is a valid lower bound of the
-  // global k-th best, so the main pass starts with a pass rate of ~k/n_sample instead of warming every
-  // candidate list up from -inf; candidates appended per row drop by an order of magnitude.
+  // The fused kernel is first run on a strided sample of the posts (a TMA view with a larger row pitch:
+  // no data is moved).  The k-th best score of the sample is a valid lower bound of the global k-th
+  // best, so the main pass starts with a pass rate of ~k/n_sample instead of warming every candidate
+  // list up from -inf; candidates appended per row drop by an order of magnitude.
   if (L.has_sample) {
     const int64_t n_s = L.n_s, stride = L.stride;
     const Plan& ps = L.sample;
@@ -814,48 +849,66 @@ int frx_score_topk(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* pos
     S.index_base = 0;
     S.cap = ps.cap;
     S.keep_limit = ps.keep_limit;
-    rc = launch_score<MODE_TOPK>(brand_bf16, ld_a, post_bf16, ld_b * stride, nb, n_s, d, ps, S, st, false);
+    rc = launch_score<MODE_TOPK, TF32>(a, ld_a, b, ld_b * stride, nb, n_s, d, ps, S, st, false);
     if (rc) return rc;
     rc = run_merge(ps);
     if (rc) return rc;
     seed_threshold_kernel<<<(nb + 255) / 256, 256, 0, st>>>(topk_scores, nb, k, P.row_thr);
     FRX_LAUNCH_CHECK();
   }
-  rc = launch_score<MODE_TOPK>(brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, plan, P, st);
+  rc = launch_score<MODE_TOPK, TF32>(a, ld_a, b, ld_b, nb, n_posts, d, plan, P, st);
   if (rc) return rc;
   rc = run_merge(plan);
   if (rc) return rc;
-  if (dense_out) return frx_score_dense(brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, dense_out, ld_dense, stream);
+  if (dense_out) return score_dense_impl<TF32>(a, ld_a, b, ld_b, nb, n_posts, d, dense_out, ld_dense, stream);
   return FRX_OK;
+}
+
+}  // namespace frx
+
+extern "C" {
+
+size_t frx_score_topk_workspace_bytes(int nb, int64_t n_posts, int d, int k) {
+  (void)d;
+  if (nb <= 0 || n_posts <= 0 || k <= 0 || k > 1024) return 0;
+  return frx::make_topk_layout(nb, n_posts, k).total();
+}
+
+int frx_score_topk(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* post_bf16, int64_t ld_b, int nb,
+                   int64_t n_posts, int d, int k, const int32_t* labels, int64_t index_base, float* topk_scores,
+                   int32_t* topk_index, float* pos_score, float* dense_out, int64_t ld_dense, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  return frx::score_topk_impl<false>(brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, k, labels, index_base, topk_scores,
+                                     topk_index, pos_score, dense_out, ld_dense, workspace, workspace_bytes, stream);
+}
+int frx_score_topk_tf32(const float* brand_f32, int64_t ld_a, const float* post_f32, int64_t ld_b, int nb,
+                        int64_t n_posts, int d, int k, const int32_t* labels, int64_t index_base, float* topk_scores,
+                        int32_t* topk_index, float* pos_score, float* dense_out, int64_t ld_dense, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  return frx::score_topk_impl<true>(brand_f32, ld_a, post_f32, ld_b, nb, n_posts, d, k, labels, index_base, topk_scores,
+                                    topk_index, pos_score, dense_out, ld_dense, workspace, workspace_bytes, stream);
 }
 
 int frx_score_dense(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* post_bf16, int64_t ld_b, int nb,
                     int64_t n_posts, int d, float* dense_out, int64_t ld_dense, void* stream) {
-  using namespace frx;
-  int rc = check_operands("frx_score_dense", brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, 0);
-  if (rc) return rc;
-  FRX_CHECK_ARG(dense_out && ld_dense >= n_posts, "frx_score_dense: bad output");
-  Plan plan = make_plan(nb, n_posts, 1, MODE_DENSE);
-  ScoreParams P{};
-  P.dense = dense_out;
-  P.ld_dense = ld_dense;
-  return launch_score<MODE_DENSE>(brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, plan, P, (cudaStream_t)stream);
+  return frx::score_dense_impl<false>(brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, dense_out, ld_dense, stream);
+}
+int frx_score_dense_tf32(const float* brand_f32, int64_t ld_a, const float* post_f32, int64_t ld_b, int nb,
+                         int64_t n_posts, int d, float* dense_out, int64_t ld_dense, void* stream) {
+  return frx::score_dense_impl<true>(brand_f32, ld_a, post_f32, ld_b, nb, n_posts, d, dense_out, ld_dense, stream);
 }
 
 int frx_score_count(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* post_bf16, int64_t ld_b, int nb,
                     int64_t n_posts, int d, int64_t index_base, const float* thr_score, const int32_t* thr_index,
                     unsigned long long* count_out, void* stream) {
-  using namespace frx;
-  int rc = check_operands("frx_score_count", brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, index_base);
-  if (rc) return rc;
-  FRX_CHECK_ARG(thr_score && thr_index && count_out, "frx_score_count: NULL pointer");
-  Plan plan = make_plan(nb, n_posts, 1, MODE_COUNT);
-  ScoreParams P{};
-  P.index_base = index_base;
-  P.thr_score = thr_score;
-  P.thr_index = thr_index;
-  P.count_out = count_out;
-  return launch_score<MODE_COUNT>(brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, plan, P, (cudaStream_t)stream);
+  return frx::score_count_impl<false>(brand_bf16, ld_a, post_bf16, ld_b, nb, n_posts, d, index_base, thr_score, thr_index,
+                                      count_out, stream);
+}
+int frx_score_count_tf32(const float* brand_f32, int64_t ld_a, const float* post_f32, int64_t ld_b, int nb,
+                         int64_t n_posts, int d, int64_t index_base, const float* thr_score, const int32_t* thr_index,
+                         unsigned long long* count_out, void* stream) {
+  return frx::score_count_impl<true>(brand_f32, ld_a, post_f32, ld_b, nb, n_posts, d, index_base, thr_score, thr_index,
+                                     count_out, stream);
 }
 
 int frx_probe_enable(int on) {

@@ -89,12 +89,20 @@ def brand_embed(w, e, brand_ids=None, nb=None):
 
 
 # ---------------------------------------------------------------------------------------------
-def _operands(brand_bf16, post_bf16, d):
-    _req(brand_bf16, torch.bfloat16, "brand_bf16", 2)
-    _req(post_bf16, torch.bfloat16, "post_bf16", 2)
+def _operands(brand_op, post_op, d):
+    """Operands are both bf16 (default precision) or both fp32 (tf32 tensor-core path)."""
+    dt = post_op.dtype if isinstance(post_op, torch.Tensor) else None
+    if dt not in (torch.bfloat16, torch.float32):
+        raise TypeError("score operands must be bfloat16 or float32 CUDA tensors")
+    _req(brand_op, dt, "brand operand", 2)
+    _req(post_op, dt, "post operand", 2)
     if d is None:
-        d = min(brand_bf16.shape[1], post_bf16.shape[1])
+        d = min(brand_op.shape[1], post_op.shape[1])
     return d
+
+
+def _variant(lib, name, post_op):
+    return getattr(lib, name + ("_tf32" if post_op.dtype == torch.float32 else ""))
 
 
 def score_topk(brand_bf16, post_bf16, k, d=None, labels=None, index_base=0, workspace=None, dense=False):
@@ -115,7 +123,7 @@ def score_topk(brand_bf16, post_bf16, k, d=None, labels=None, index_base=0, work
         pos_score = torch.empty(n_posts, dtype=torch.float32, device=dev)
     dense_out = torch.empty((nb, n_posts), dtype=torch.float32, device=dev) if dense else None
     with torch.cuda.device(dev):
-        rc = lib.frx_score_topk(_ptr(brand_bf16), brand_bf16.stride(0), _ptr(post_bf16), post_bf16.stride(0), nb,
+        rc = _variant(lib, "frx_score_topk", post_bf16)(_ptr(brand_bf16), brand_bf16.stride(0), _ptr(post_bf16), post_bf16.stride(0), nb,
                                 n_posts, d, k, _ptr(labels), index_base, _ptr(scores), _ptr(index), _ptr(pos_score),
                                 _ptr(dense_out), n_posts, _ptr(workspace), workspace.numel(), _stream(post_bf16))
     _lib.check(rc, "frx_score_topk")
@@ -129,7 +137,7 @@ def score_dense(brand_bf16, post_bf16, d=None, out=None):
     if out is None:
         out = torch.empty((nb, n_posts), dtype=torch.float32, device=post_bf16.device)
     with torch.cuda.device(post_bf16.device):
-        rc = lib.frx_score_dense(_ptr(brand_bf16), brand_bf16.stride(0), _ptr(post_bf16), post_bf16.stride(0), nb,
+        rc = _variant(lib, "frx_score_dense", post_bf16)(_ptr(brand_bf16), brand_bf16.stride(0), _ptr(post_bf16), post_bf16.stride(0), nb,
                                  n_posts, d, _ptr(out), out.stride(0), _stream(post_bf16))
     _lib.check(rc, "frx_score_dense")
     return out
@@ -145,7 +153,7 @@ def score_count(brand_bf16, post_bf16, thr_score, thr_index, d=None, index_base=
     if out is None:
         out = torch.zeros(nb, dtype=torch.int64, device=post_bf16.device)
     with torch.cuda.device(post_bf16.device):
-        rc = lib.frx_score_count(_ptr(brand_bf16), brand_bf16.stride(0), _ptr(post_bf16), post_bf16.stride(0), nb,
+        rc = _variant(lib, "frx_score_count", post_bf16)(_ptr(brand_bf16), brand_bf16.stride(0), _ptr(post_bf16), post_bf16.stride(0), nb,
                                  n_posts, d, index_base, _ptr(thr_score), _ptr(thr_index), _ptr(out),
                                  _stream(post_bf16))
     _lib.check(rc, "frx_score_count")

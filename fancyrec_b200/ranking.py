@@ -14,8 +14,16 @@ MIN_TOPK = 64
 DENSE_BUDGET_BYTES = 2 << 30
 
 
-def to_operand(x_f32, final_norm=True):
-    """fp32 [N, D] embeddings -> L2-normalised bf16 operand [N, round_up(D, 64)] (zero padded)."""
+PRECISION = "bf16"      # "bf16" (default: 1e-3 score tolerance, full tensor rate) or "tf32" (2e-5, half rate)
+
+
+def to_operand(x_f32, final_norm=True, precision=None):
+    """fp32 [N, D] embeddings -> L2-normalised score operand: bf16 [N, round_up(D, 64)] (zero padded), or
+    fp32 [N, D] for the tf32 tensor-core path (D % 4 == 0)."""
+    if (precision or PRECISION) == "tf32":
+        if x_f32.shape[1] % 4:
+            raise ValueError("tf32 operands need D % 4 == 0")
+        return ops.finalize_posts(x_f32, final_norm=final_norm, want_f32=True, want_bf16=False)[0]
     return ops.finalize_posts(x_f32, final_norm=final_norm, want_f32=False, want_bf16=True)[1]
 
 

@@ -127,6 +127,22 @@ int frx_score_count(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* po
                     const float* thr_score, const int32_t* thr_index,
                     unsigned long long* count_out, void* stream);
 
+/* tf32 variants: identical contracts, operands are fp32 [rows, ld] (rows L2-normalised, ld % 4 == 0, 16-byte aligned base),
+ * read by the tensor cores as tf32 (10-bit mantissa, tcgen05.mma.kind::tf32) with fp32 accumulation: scores within 2e-5 of
+ * fp32 cal_sim at D >= 1024 on the cosine scale, at half the bf16 tensor throughput and twice the operand bytes. */
+int frx_score_topk_tf32(const float* brand_f32, int64_t ld_a, const float* post_f32, int64_t ld_b,
+                        int nb, int64_t n_posts, int d, int k,
+                        const int32_t* labels, int64_t index_base,
+                        float* topk_scores, int32_t* topk_index, float* pos_score,
+                        float* dense_out, int64_t ld_dense,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int frx_score_dense_tf32(const float* brand_f32, int64_t ld_a, const float* post_f32, int64_t ld_b,
+                         int nb, int64_t n_posts, int d, float* dense_out, int64_t ld_dense, void* stream);
+int frx_score_count_tf32(const float* brand_f32, int64_t ld_a, const float* post_f32, int64_t ld_b,
+                         int nb, int64_t n_posts, int d, int64_t index_base,
+                         const float* thr_score, const int32_t* thr_index,
+                         unsigned long long* count_out, void* stream);
+
 /* Merge G candidate lists per brand (the multi-GPU exchange step after the all-gather):
  * in_scores / in_index [g, nb, k_in] -> out [nb, k_out], same order; entries with index < 0 are
  * padding.  Requires g * k_in <= 16384. */

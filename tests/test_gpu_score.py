@@ -82,6 +82,36 @@ def test_sample_seeded_thresholds_large_np(kind, k):
     assert np.array_equal(res["pos_score"].cpu().numpy(), dense[lab, np.arange(npost)])
 
 
+@pytest.mark.parametrize("nb,npost,d,k", [(130, 3000, 1024, 100), (40, 300000, 64, 64), (7, 513, 52, 10)])
+def test_tf32_path(nb, npost, d, k):
+    """fp32 operands through tcgen05.mma.kind::tf32: tighter score tolerance, same exact ranking contract."""
+    from fancyrec_b200 import ops, ranking
+    rs = np.random.RandomState(nb + d)
+    brand = rs.standard_normal((nb, d)).astype(np.float32)
+    posts = rs.standard_normal((npost, d)).astype(np.float32)
+    lab = synth.labels(3, npost, nb)
+    a = ranking.to_operand(to_dev(brand), precision="tf32")
+    b = ranking.to_operand(to_dev(posts), precision="tf32")
+    assert a.dtype == torch.float32
+    dense = ops.score_dense(a, b, d=d).cpu().numpy()
+    ref = oref.cal_sim(brand, posts)
+    # tf32 keeps 10 mantissa bits (operands truncated by the tensor core): <= 2 * 2^-10 worst case on the
+    # cosine scale; 5e-5 at D >= 1024 where the errors average out (stated tf32 tolerance; observed ~1e-5)
+    err = float(np.abs(dense - ref).max())
+    print("tf32 max |score - fp32 cal_sim| at D=%d: %.3e" % (d, err))
+    assert err <= (5e-5 if d >= 1024 else 2.0 ** -9)
+    res = ops.score_topk(a, b, k, d=d, labels=to_dev(lab.astype(np.int32)), index_base=5)
+    want = oref.topk_indices(dense, k)
+    assert np.array_equal(res["index"].cpu().numpy(), want + 5)
+    assert np.array_equal(res["scores"].cpu().numpy(), np.take_along_axis(dense, want, 1))
+    assert np.array_equal(res["pos_score"].cpu().numpy(), dense[lab, np.arange(npost)])
+    tj = rs.randint(0, npost, nb)
+    cnt = ops.score_count(a, b, to_dev(dense[np.arange(nb), tj].copy()), to_dev((tj + 5).astype(np.int32)), d=d,
+                          index_base=5).cpu().numpy()
+    for r in range(0, nb, max(1, nb // 8)):
+        assert cnt[r] == int(np.where(oref.order_desc(dense[r]) == tj[r])[0][0])
+
+
 def test_heavy_ties_and_index_base():
     """Quantised scores (few distinct values) -> the tie-break carries the whole ranking."""
     rs = np.random.RandomState(3)
