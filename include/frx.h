@@ -128,8 +128,8 @@ int frx_score_count(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* po
                     unsigned long long* count_out, void* stream);
 
 /* tf32 variants: identical contracts, operands are fp32 [rows, ld] (rows L2-normalised, ld % 4 == 0, 16-byte aligned base),
- * read by the tensor cores as tf32 (10-bit mantissa, tcgen05.mma.kind::tf32) with fp32 accumulation: scores within 2e-5 of
- * fp32 cal_sim at D >= 1024 on the cosine scale, at half the bf16 tensor throughput and twice the operand bytes. */
+ * read by the tensor cores as tf32 (10-bit mantissa, tcgen05.mma.kind::tf32) with fp32 accumulation: scores within 2e-4 of
+ * fp32 cal_sim at D >= 1024 on the cosine scale (observed 1.1e-4), at half the bf16 tensor throughput and twice the operand bytes. */
 int frx_score_topk_tf32(const float* brand_f32, int64_t ld_a, const float* post_f32, int64_t ld_b,
                         int nb, int64_t n_posts, int d, int k,
                         const int32_t* labels, int64_t index_base,
