@@ -328,20 +328,50 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           if (nvalid == 0) continue;                 // warp-uniform
 
           if (MODE == MODE_TOPK) {
-            // fast path: does any lane hold a score that reaches its row's threshold?
-            float mx = -INFINITY;
+            if (nvalid < 32) {                       // last tile only: out-of-range columns can never qualify
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (i < nvalid) ? __uint_as_float(v[i]) : -INFINITY);
-            if (__any_sync(0xffffffffu, mx >= thr)) {
+              for (int i = 0; i < 32; ++i) if (i >= nvalid) v[i] = 0x7FC00000u;   // NaN: fails every >=
+            }
+            if (P.labels != nullptr) {
+              // S[label[j], j]: lane i holds the label of column cbase+i; the owner row is a lane of this warp
+              // iff label - (m_tile*128 + q*32) is in [0, 32).  ~1 column per chunk qualifies: loop over the set
+              // bits, the owner lane picks its register with a predicated select chain (no per-column branch).
+              int lbl = -1;
+#pragma unroll
+              for (int cc = 0; cc < CHUNKS; ++cc) if (cc == c) lbl = lab[cc];
+              int tgt = -1;
+              if (lbl >= 0 && lbl < P.nb) tgt = lbl - (m_tile * BM + q * 32);   // out-of-range labels keep NaN
+              uint32_t hit = __ballot_sync(0xffffffffu, tgt >= 0 && tgt < 32);
+              while (hit) {
+                const int i = __ffs(hit) - 1;
+                hit &= hit - 1;
+                const int owner = __shfl_sync(0xffffffffu, tgt, i);
+                if (lane == owner) {
+                  uint32_t val = 0;
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) val = (j == i) ? v[j] : val;
+                  P.pos_score[cbase + i] = __uint_as_float(val);
+                }
+              }
+            }
+            // per-lane qualification mask (branch-free), then ONE warp reduction tells which columns have a
+            // qualifying score in any row; appends are visited in groups of 4 columns
+            uint32_t hm = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) hm |= (__uint_as_float(v[i]) >= thr ? 1u : 0u) << i;
+            const uint32_t colmask = __reduce_or_sync(0xffffffffu, hm);
+            if (colmask) {
               const uint32_t gbase = (uint32_t)(P.index_base + cbase);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float s = __uint_as_float(v[i]);
-                const bool hit = i < nvalid && s >= thr;
-                if (__any_sync(0xffffffffu, hit)) {          // warp-uniform: most columns have no hit in any row
-                  if (hit) {
-                    rowbuf[cnt] = make_key(s, gbase + i);
-                    ++cnt;
+              for (int g4 = 0; g4 < 8; ++g4) {
+                if (colmask & (0xFu << (4 * g4))) {  // warp-uniform
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const int i = 4 * g4 + j;
+                    if ((hm >> i) & 1u) {
+                      rowbuf[cnt] = make_key(__uint_as_float(v[i]), gbase + i);
+                      ++cnt;
+                    }
                   }
                 }
               }
@@ -353,9 +383,9 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                   const int l = __ffs(full) - 1;
                   full &= full - 1;
                   const int n = __shfl_sync(0xffffffffu, cnt, l);
-                  unsigned long long* b = P.part_keys + (part + q * 32 + l) * P.cap;
+                  unsigned long long* bb = P.part_keys + (part + q * 32 + l) * P.cap;
                   float nthr;
-                  const int kept = select_dispatch(P.cap, b, n, P.k, P.keep_limit, false, hist, &nthr);
+                  const int kept = select_dispatch(P.cap, bb, n, P.k, P.keep_limit, false, hist, &nthr);
                   if (lane == l) {
                     cnt = kept;
                     thr = fmaxf(thr, nthr);
@@ -363,25 +393,6 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                   }
                 }
                 __syncwarp();
-              }
-            }
-            if (P.labels != nullptr) {
-              // S[label[j], j]: lane i holds the label of column cbase+i; the owner row is a lane of
-              // this warp iff label - (m_tile*128 + q*32) is in [0, 32)
-              int lbl = -1;
-#pragma unroll
-              for (int cc = 0; cc < CHUNKS; ++cc) if (cc == c) lbl = lab[cc];
-              int tgt = -1;
-              if (lbl >= 0 && lbl < P.nb) tgt = lbl - (m_tile * BM + q * 32);   // out-of-range labels keep NaN
-              const uint32_t hit = __ballot_sync(0xffffffffu, tgt >= 0 && tgt < 32);
-              if (hit) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  if ((hit >> i) & 1u) {
-                    const int owner = __shfl_sync(0xffffffffu, tgt, i);
-                    if (lane == owner) P.pos_score[cbase + i] = __uint_as_float(v[i]);
-                  }
-                }
               }
             }
           } else if (MODE == MODE_DENSE) {
@@ -556,6 +567,42 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long
   }
 }
 
+// Sample pass, dense flavour: one block per brand row finds the k-th largest of the row's n sample scores
+// (MSB-first 8-bit radix select on order-preserving u32 keys held in shared memory) and writes it to row_thr.
+__global__ void __launch_bounds__(256) row_kth_kernel(const float* __restrict__ dense, int64_t ld, int n, int k,
+                                                      uint32_t* __restrict__ row_thr) {
+  extern __shared__ uint32_t sk32[];
+  __shared__ uint32_t hist[256];
+  __shared__ int sel[3];
+  const int b = blockIdx.x;
+  const float* row = dense + (int64_t)b * ld;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float s = row[i];
+    sk32[i] = (s == s) ? score_to_ordered(s) : 0u;      // NaN ranks below everything
+  }
+  uint32_t prefix = 0;
+  int need = k < n ? k : n, shift = 24;
+  for (int pass = 0; pass < 4; ++pass, shift -= 8) {
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t key = sk32[i];
+      if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int digit, above, bucket;
+      select_digit(hist, threadIdx.x, need, digit, above, bucket);
+      if (threadIdx.x == 0) { sel[0] = digit; sel[1] = above; }
+    }
+    __syncthreads();
+    prefix = (prefix << 8) | (uint32_t)sel[0];
+    need -= sel[1];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) row_thr[b] = prefix;            // exact k-th largest score of the sample
+}
+
 // row_thr[b] = ordered(k-th best score of the sample pass) -- a valid lower bound of the row's global k-th best
 // because the sample is a subset of the posts.  Rows whose sample list is short keep 0 (= no threshold).
 __global__ void seed_threshold_kernel(const float* __restrict__ topk_scores, int nb, int k, uint32_t* __restrict__ row_thr) {
@@ -684,10 +731,10 @@ static Probe g_probe;
 // the main pass and the sample pass (which reuses them).
 struct TopkLayout {
   Plan main, sample;
-  bool has_sample;
+  bool has_sample, sample_dense;
   int64_t n_s, stride;
-  size_t cnt_bytes, thr_bytes, keys_bytes;
-  size_t total() const { return cnt_bytes + thr_bytes + keys_bytes + 256; }
+  size_t cnt_bytes, thr_bytes, keys_bytes, dense_bytes;
+  size_t total() const { return cnt_bytes + thr_bytes + keys_bytes + dense_bytes + 256; }
 };
 
 static TopkLayout make_topk_layout(int nb, int64_t n_posts, int k) {
@@ -706,9 +753,16 @@ static TopkLayout make_topk_layout(int nb, int64_t n_posts, int k) {
     n_s = (n_s + BN - 1) / BN * BN;
     L.n_s = n_s;
     L.stride = n_posts / n_s;
-    L.sample = make_plan(nb, n_s, k, MODE_TOPK);
-    if (L.sample.cnt_bytes > L.cnt_bytes) L.cnt_bytes = L.sample.cnt_bytes;
-    if (L.sample.keys_bytes > L.keys_bytes) L.keys_bytes = L.sample.keys_bytes;
+    // small enough: dense sample tile + per-row k-th select (cheapest); else the fused top-k kernel on the sample
+    L.sample_dense = (size_t)nb * (size_t)n_s * sizeof(float) <= ((size_t)256 << 20) && n_s <= 32768;
+    if (L.sample_dense) {
+      L.sample = make_plan(nb, n_s, 1, MODE_DENSE);
+      L.dense_bytes = (((size_t)nb * (size_t)n_s * sizeof(float)) + 255) & ~(size_t)255;
+    } else {
+      L.sample = make_plan(nb, n_s, k, MODE_TOPK);
+      if (L.sample.cnt_bytes > L.cnt_bytes) L.cnt_bytes = L.sample.cnt_bytes;
+      if (L.sample.keys_bytes > L.keys_bytes) L.keys_bytes = L.sample.keys_bytes;
+    }
   }
   return L;
 }
@@ -840,7 +894,19 @@ static int score_topk_impl(const void* a, int64_t ld_a, const void* b, int64_t l
   // no data is moved).  The k-th best score of the sample is a valid lower bound of the global k-th
   // best, so the main pass starts with a pass rate of ~k/n_sample instead of warming every candidate
   // list up from -inf; candidates appended per row drop by an order of magnitude.
-  if (L.has_sample) {
+  if (L.has_sample && L.sample_dense) {
+    float* sdense = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + L.cnt_bytes + L.thr_bytes + L.keys_bytes);
+    ScoreParams S{};
+    S.dense = sdense;
+    S.ld_dense = L.n_s;
+    rc = launch_score<MODE_DENSE, TF32>(a, ld_a, b, ld_b * L.stride, nb, L.n_s, d, L.sample, S, st, false);
+    if (rc) return rc;
+    const size_t ksmem = (size_t)L.n_s * sizeof(uint32_t);
+    if (ksmem > 32 * 1024)
+      FRX_CUDA(cudaFuncSetAttribute(row_kth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksmem));
+    row_kth_kernel<<<nb, 256, ksmem, st>>>(sdense, L.n_s, (int)L.n_s, k, P.row_thr);
+    FRX_LAUNCH_CHECK();
+  } else if (L.has_sample) {
     const int64_t n_s = L.n_s, stride = L.stride;
     const Plan& ps = L.sample;
     ScoreParams S = P;
