@@ -497,16 +497,17 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long
   __shared__ int sel[3];
   const int b = blockIdx.x, m_tile = b / BM, r = b % BM;
   const int lists = splits * 2;                 // (split, column half) -> list (split*num_m_tiles + m_tile)*2 + half
+  // list sizes: loaded in parallel (one L2 round trip), then a serial prefix over shared memory
+  for (int s = threadIdx.x; s < lists; s += blockDim.x)
+    offs[s + 1] = part_cnt[(((size_t)(s >> 1) * num_m_tiles + m_tile) * 2 + (s & 1)) * BM + r];
+  __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int s = 0; s < lists; ++s) {
-      offs[s] = acc;
-      acc += part_cnt[(((size_t)(s >> 1) * num_m_tiles + m_tile) * 2 + (s & 1)) * BM + r];
-    }
-    offs[lists] = acc;
+    offs[0] = 0;
+    for (int s = 0; s < lists; ++s) { acc += offs[s + 1]; offs[s + 1] = acc; }
+    kept = 0;
   }
   __syncthreads();
-  if (threadIdx.x == 0) kept = 0;
   for (int s = 0; s < lists; ++s) {
     const int n = offs[s + 1] - offs[s];
     const unsigned long long* src = part_keys + ((((size_t)(s >> 1) * num_m_tiles + m_tile) * 2 + (s & 1)) * BM + r) * cap;
