@@ -484,19 +484,26 @@ __device__ __forceinline__ int next_pow2(int v) {
   return p;
 }
 
-// One block per brand: gather the per-split candidate lists of this row, sort, emit the top-k.
+// One block per brand: gather the per-split candidate lists of this row, select + sort, emit the top-k.
+// Candidates are staged in shared memory when they fit (`smem_keys` entries incl. room for the k survivors);
+// otherwise (large k x many lists) the radix-select passes stream them from global memory through a
+// flattened index (binary search over the list offsets), 8 independent loads in flight per thread.
 __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long long* __restrict__ part_keys,
                                                              const int* __restrict__ part_cnt,
                                                              const uint32_t* __restrict__ row_thr, int num_m_tiles,
-                                                             int splits, int cap, int k, float* __restrict__ out_s,
-                                                             int32_t* __restrict__ out_i) {
+                                                             int splits, int cap, int k, int smem_keys,
+                                                             float* __restrict__ out_s, int32_t* __restrict__ out_i) {
   extern __shared__ unsigned long long skeys[];
   __shared__ int offs[2049];
   __shared__ int kept;
   __shared__ uint32_t hist[256];
   __shared__ int sel[3];
+  (void)row_thr;
   const int b = blockIdx.x, m_tile = b / BM, r = b % BM;
   const int lists = splits * 2;                 // (split, column half) -> list (split*num_m_tiles + m_tile)*2 + half
+  auto list_ptr = [&](int s) {
+    return part_keys + ((((size_t)(s >> 1) * num_m_tiles + m_tile) * 2 + (s & 1)) * BM + r) * cap;
+  };
   // list sizes: loaded in parallel (one L2 round trip), then a serial prefix over shared memory
   for (int s = threadIdx.x; s < lists; s += blockDim.x)
     offs[s + 1] = part_cnt[(((size_t)(s >> 1) * num_m_tiles + m_tile) * 2 + (s & 1)) * BM + r];
@@ -508,24 +515,44 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long
     kept = 0;
   }
   __syncthreads();
-  for (int s = 0; s < lists; ++s) {
-    const int n = offs[s + 1] - offs[s];
-    const unsigned long long* src = part_keys + ((((size_t)(s >> 1) * num_m_tiles + m_tile) * 2 + (s & 1)) * BM + r) * cap;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) skeys[offs[s] + i] = src[i];
-  }
-  __syncthreads();
   int total = offs[lists];
-  // More than k candidates: block-wide MSB-first radix select of the k-th best key (exact), then only the
-  // k survivors are sorted -- instead of bitonic-sorting all splits * 2 * k keys.
+  const bool staged = total + (total > k ? k : 0) <= smem_keys;
+  // flattened element g -> key (global path)
+  auto fetch = [&](int g) -> unsigned long long {
+    int lo = 0, hi = lists;                      // largest s with offs[s] <= g
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offs[mid] <= g) lo = mid; else hi = mid; }
+    return __ldcg(list_ptr(lo) + (g - offs[lo]));
+  };
+  if (staged) {
+    for (int s = 0; s < lists; ++s) {
+      const int n = offs[s + 1] - offs[s];
+      const unsigned long long* src = list_ptr(s);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) skeys[offs[s] + i] = src[i];
+    }
+    __syncthreads();
+  }
   if (total > k) {
+    // block-wide MSB-first radix select of the k-th best key (exact; keys are unique)
     unsigned long long prefix = 0;
     int need = k, shift = 56;
     for (int pass = 0; pass < 8; ++pass, shift -= 8) {
       if (threadIdx.x < 256) hist[threadIdx.x] = 0;
       __syncthreads();
-      for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const unsigned long long key = skeys[i];
-        if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
+      if (staged) {
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+          const unsigned long long key = skeys[i];
+          if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
+        }
+      } else {
+        for (int g0 = threadIdx.x; g0 < total; g0 += 8 * 256) {
+          unsigned long long kk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const int g = g0 + j * 256; kk[j] = g < total ? fetch(g) : 0ull; }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (g0 + j * 256 < total && (pass == 0 || (kk[j] >> (shift + 8)) == prefix))
+              atomicAdd(&hist[(uint32_t)(kk[j] >> shift) & 255u], 1u);
+        }
       }
       __syncthreads();
       if (threadIdx.x < 32) {
@@ -538,21 +565,36 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long
       need -= sel[1];
       const int bucket = sel[2];
       __syncthreads();
-      if (bucket == 1 || pass == 7) break;        // keys are unique: a singleton bucket pins the k-th key
+      if (bucket == 1 || pass == 7) break;        // a singleton bucket pins the k-th key
     }
     const unsigned long long thr_key = prefix << shift;
-    // survivors (exactly k) go to the tail region of skeys, then are moved to the front
-    unsigned long long* dst = skeys + total;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-      const unsigned long long key = skeys[i];
-      if (key >= thr_key) dst[atomicAdd(&kept, 1)] = key;
+    // the k survivors: staged -> tail region of skeys then moved to the front; global -> straight into skeys
+    unsigned long long* dst = staged ? skeys + total : skeys;
+    if (staged) {
+      for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const unsigned long long key = skeys[i];
+        if (key >= thr_key) dst[atomicAdd(&kept, 1)] = key;
+      }
+    } else {
+      for (int g0 = threadIdx.x; g0 < total; g0 += 8 * 256) {
+        unsigned long long kk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int g = g0 + j * 256; kk[j] = g < total ? fetch(g) : 0ull; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (g0 + j * 256 < total && kk[j] >= thr_key) dst[atomicAdd(&kept, 1)] = kk[j];
+      }
     }
     __syncthreads();
     const int nk = kept;
-    for (int i = threadIdx.x; i < nk; i += blockDim.x) { const unsigned long long key = dst[i]; skeys[i] = key; }
-    // (reads of dst[i] and writes of skeys[i] never alias: dst starts at total >= nk)
-    __syncthreads();
+    if (staged) {
+      for (int i = threadIdx.x; i < nk; i += blockDim.x) { const unsigned long long key = dst[i]; skeys[i] = key; }
+      __syncthreads();                            // dst starts at total >= nk: reads and writes never alias
+    }
     total = nk;
+  } else if (!staged) {
+    for (int g = threadIdx.x; g < total; g += blockDim.x) skeys[g] = fetch(g);
+    __syncthreads();
   }
   const int np2 = next_pow2(total > 1 ? total : 2);
   for (int i = total + threadIdx.x; i < np2; i += blockDim.x) skeys[i] = 0ull;
@@ -694,7 +736,6 @@ static Plan make_plan(int nb, int64_t n_posts, int k, int mode) {
   p.num_m_tiles = (nb + BM - 1) / BM;
   p.num_n_tiles = (n_posts + BN - 1) / BN;
   int64_t smax = p.num_n_tiles;
-  if (mode == MODE_TOPK && smax > MAX_MERGE_KEYS / (2 * k)) smax = MAX_MERGE_KEYS / (2 * k);   // 2 lists per split
   if (smax > 1024) smax = 1024;
   if (smax < 1) smax = 1;
   // pick the split count that fills whole waves of `sms` CTAs; prefer fewer, longer items
@@ -878,15 +919,19 @@ static int score_topk_impl(const void* a, int64_t ld_a, const void* b, int64_t l
   P.pos_score = pos_score;
   if (pos_score) FRX_CUDA(cudaMemsetAsync(pos_score, 0xFF, (size_t)n_posts * sizeof(float), st));   // NaN
   auto run_merge = [&](const Plan& pl) -> int {
-    const int total_max = pl.splits * 2 * k;
-    int np2 = 2;
-    while (np2 < 2 * k) np2 <<= 1;                                 // sort buffer when nothing needs selecting
-    const size_t mkeys = (size_t)(total_max + k) > (size_t)np2 ? (size_t)(total_max + k) : (size_t)np2;
+    // shared memory: every candidate + the k survivors when that fits MAX_MERGE_KEYS, else just the sort buffer
+    // (>= 2k keys) and the kernel streams the candidates from global memory
+    const size_t total_max = (size_t)pl.splits * 2 * (size_t)k;
+    size_t np2 = 2;
+    while (np2 < (size_t)2 * k) np2 <<= 1;
+    size_t mkeys = total_max + k;
+    if (mkeys > (size_t)MAX_MERGE_KEYS + 1024) mkeys = np2;
+    if (mkeys < np2) mkeys = np2;
     const size_t msmem = mkeys * sizeof(unsigned long long);
     if (msmem > 32 * 1024)   // static smem (~10 KB) counts against the 48 KB default too
       FRX_CUDA(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
     merge_partials_kernel<<<nb, 256, msmem, st>>>(P.part_keys, P.part_cnt, P.row_thr, pl.num_m_tiles, pl.splits, pl.cap, k,
-                                                  topk_scores, topk_index);
+                                                  (int)mkeys, topk_scores, topk_index);
     FRX_LAUNCH_CHECK();
     return FRX_OK;
   };
