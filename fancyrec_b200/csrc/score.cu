@@ -791,6 +791,7 @@ static TopkLayout make_topk_layout(int nb, int64_t n_posts, int k) {
     n_s = n_s < 8192 ? 8192 : (n_s > 32768 ? 32768 : n_s);
     if (n_s < 32 * (int64_t)k) n_s = 32 * (int64_t)k;          // keep the seeded pass rate k / n_s at <= 3 %
     if (n_s > 32768) n_s = 32768;
+    if (n_s > n_posts / 16) n_s = n_posts / 16;                // never spend more than ~6 % extra on the sample
     if (n_s < 4 * (int64_t)k) n_s = 4 * (int64_t)k;
     n_s = (n_s + BN - 1) / BN * BN;
     L.n_s = n_s;
