@@ -241,8 +241,9 @@ __global__ void __launch_bounds__(256) finalize_warp_kernel(FinalizeParams P) {
 // is unchanged, but the kernel needs ~40 registers instead of ~180, so 6x more warps are resident and
 // the HBM pipe stays full while other warps are in their arithmetic / store phases.
 __device__ __forceinline__ float4 ld_row_f4(const FinalizeParams& P, int64_t p, int c) {
-  return c < P.dv ? __ldg(reinterpret_cast<const float4*>(P.visual + p * P.dv + c))
-                  : __ldg(reinterpret_cast<const float4*>(P.text + p * P.dt + (c - P.dv)));
+  // read-once data: streaming (evict-first) loads keep L2 for the stores' write-back
+  return c < P.dv ? __ldcs(reinterpret_cast<const float4*>(P.visual + p * P.dv + c))
+                  : __ldcs(reinterpret_cast<const float4*>(P.text + p * P.dt + (c - P.dv)));
 }
 
 __global__ void __launch_bounds__(256) finalize_stream_kernel(FinalizeParams P) {
