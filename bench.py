@@ -181,7 +181,17 @@ def max_over_ranks(ms, dev, world):
     return float(t.item())
 
 
+def _claim_stdout():
+    """Route fd 1 to stderr for the rest of the process (NCCL prints its version banner on stdout) and
+    return a writer for the ONE JSON line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return lambda text: os.write(saved, (text + "\n").encode())
+
+
 def run_ours(args):
+    emit = _claim_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -278,7 +288,7 @@ def run_ours(args):
             line["e2e"] = e2e
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
 
