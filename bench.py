@@ -155,9 +155,16 @@ class Evaluator:
 
     def step(self, w, e, labels, visual, text):
         ops = self.ops
-        brand = ops.brand_embed(w, e, nb=self.nb)                                      # 1 kernel
-        brand_op = ops.finalize_posts(brand, final_norm=True)[1]                        # 1
+        # brand side (FMA-bound, 0.5 ms) on a second stream, concurrent with the HBM-bound post finalisation
+        main = torch.cuda.current_stream(self.dev)
+        side = self.ranking.side_stream(self.dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            brand = ops.brand_embed(w, e, nb=self.nb)                                  # 1 kernel
+            brand_op = ops.finalize_posts(brand, final_norm=True)[1]                    # 1
         post_op = ops.finalize_posts(visual, text, visual_norm=True, text_norm=True, final_norm=True)[1]   # 1
+        main.wait_stream(side)
+        brand.record_stream(main); brand_op.record_stream(main)
         st = self.sharded.sharded_rank_statistics(brand_op, post_op, labels, self.d, self.cfg["k"], self.n_total,
                                                   workspace=self.workspace)
         self.workspace = st["workspace"]

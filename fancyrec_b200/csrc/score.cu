@@ -628,9 +628,14 @@ __global__ void __launch_bounds__(256) row_kth_kernel(const float* __restrict__ 
   for (int pass = 0; pass < 4; ++pass, shift -= 8) {
     if (threadIdx.x < 256) hist[threadIdx.x] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint32_t key = sk32[i];
-      if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    const int n_round = (n + 255) & ~255;                 // whole warps stay converged for match_any
+    for (int i = threadIdx.x; i < n_round; i += blockDim.x) {
+      const uint32_t key = i < n ? sk32[i] : 0u;
+      const bool on = i < n && (pass == 0 || (key >> (shift + 8)) == prefix);
+      // scores cluster in a few digits (same sign/exponent): one shared-memory atomic per distinct digit per warp
+      const uint32_t digit = on ? ((key >> shift) & 255u) : 0xFFFFFFFFu;
+      const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+      if (on && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
     }
     __syncthreads();
     if (threadIdx.x < 32) {
