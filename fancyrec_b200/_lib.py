@@ -18,7 +18,8 @@ SIGNATURES = {
     "frx_last_error": (ctypes.c_char_p, []),
     "frx_device_check": (c_i32, [c_i32]),
     "frx_finalize_posts": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
-    "frx_brand_embed": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "frx_brand_embed_workspace_bytes": (c_sz, [c_i32, c_i32, c_i32]),
+    "frx_brand_embed": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_sz, c_vp]),
     "frx_score_topk_workspace_bytes": (c_sz, [c_i32, c_i64, c_i32, c_i32]),
     "frx_score_topk": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp,
                                c_vp, c_i64, c_vp, c_sz, c_vp]),

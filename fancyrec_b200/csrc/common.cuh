@@ -41,6 +41,10 @@ void set_error(const char* fmt, ...);
 
 int num_sms();
 
+// score.cu: out[m, n] = scale * sum_k A[m, k] * B[n, k], fp32 operands read as tf32, fp32 accumulation (tcgen05)
+int dense_tf32_scaled(const float* a, int64_t ld_a, const float* b, int64_t ld_b, int m, int64_t n, int k, float* out,
+                      int64_t ld_out, float scale, void* stream);
+
 // ---------------------------------------------------------------------------------------------
 // Total order used everywhere: (score descending, post index ascending).
 // A candidate is packed into one u64 key so that "larger key" == "ranks earlier":

@@ -501,6 +501,58 @@ __global__ void __launch_bounds__(256) brand_embed_kernel_128(const float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 3xTF32 brand embedding on the tensor cores: x = hi + lo with hi, lo exactly representable in tf32
+// (10-bit mantissa), and  W.E = W_hi.E_hi + W_lo.E_hi + W_hi.E_lo  (+ O(2^-22)) is ONE tf32 GEMM over the
+// K-concatenated operands  W' = [W_hi | W_lo | W_hi]  (nb x 3A)  and  E'^T = [E_hi | E_hi | E_lo]^T  (D x 3A),
+// fp32 accumulation in TMEM: fp32-grade result (~1e-6 relative) at tensor-core speed.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t u = __float_as_uint(x);
+  u += 0x00000FFFu + ((u >> 13) & 1u);          // round to nearest even at bit 13
+  return __uint_as_float(u & 0xFFFFE000u);
+}
+
+// rows of W (gathered through ids) -> [hi | lo | hi]
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ w, const int64_t* __restrict__ ids, int nb,
+                                                         int a, float* __restrict__ out) {
+  const int r = blockIdx.x;
+  const int64_t src = ids ? ids[r] : (int64_t)r;
+  for (int c = threadIdx.x; c < a; c += blockDim.x) {
+    const float x = w[src * a + c];
+    const float hi = tf32_round(x), lo = tf32_round(x - hi);
+    float* o = out + (int64_t)r * 3 * a;
+    o[c] = hi; o[a + c] = lo; o[2 * a + c] = hi;
+  }
+}
+
+// E [a, d] -> transposed and split: out[n, :] = [E_hi[:, n] | E_hi[:, n] | E_lo[:, n]]   (32x32 smem transpose)
+__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ e, int a, int d, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;    // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int k = k0 + ty + i, n = n0 + tx;
+    tile[ty + i][tx] = (k < a && n < d) ? e[(int64_t)k * d + n] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int n = n0 + ty + i, k = k0 + tx;
+    if (n < d && k < a) {
+      const float x = tile[tx][ty + i];
+      const float hi = tf32_round(x), lo = tf32_round(x - hi);
+      float* o = out + (int64_t)n * 3 * a;
+      o[k] = hi; o[a + k] = hi; o[2 * a + k] = lo;
+    }
+  }
+}
+
+static size_t brand_ws_bytes(int nb, int a, int d) {
+  return (((size_t)nb * 3 * a * sizeof(float) + 255) & ~(size_t)255) + (((size_t)d * 3 * a * sizeof(float) + 255) & ~(size_t)255);
+}
+
 }  // namespace frx
 
 extern "C" {
@@ -555,21 +607,39 @@ int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_
   return FRX_OK;
 }
 
+size_t frx_brand_embed_workspace_bytes(int nb, int a, int d) {
+  if (nb <= 0 || a <= 0 || d <= 0 || a % 4 != 0) return 0;     // 0: only the CUDA-core path is available
+  return frx::brand_ws_bytes(nb, a, d);
+}
+
 int frx_brand_embed(const float* w, int64_t w_rows, const float* e, const int64_t* brand_ids, int nb, int a, int d,
-                    float* out_f32, void* stream) {
+                    float* out_f32, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace frx;
   FRX_CHECK_ARG(w && e && out_f32, "frx_brand_embed: NULL pointer");
   FRX_CHECK_ARG(nb >= 0 && a > 0 && d > 0, "frx_brand_embed: bad sizes nb=%d a=%d d=%d", nb, a, d);
   FRX_CHECK_ARG(brand_ids != nullptr || nb <= w_rows, "frx_brand_embed: nb=%d exceeds table rows %lld", nb, (long long)w_rows);
   if (nb == 0) return FRX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  // tensor-core path (3xTF32) when the caller provides scratch and the problem is worth a GEMM launch
+  if (workspace != nullptr && a % 4 == 0 && workspace_bytes >= brand_ws_bytes(nb, a, d) &&
+      (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (long)nb * d >= 128 * 256) {
+    float* wsplit = reinterpret_cast<float*>(workspace);
+    float* esplit = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) +
+                                             (((size_t)nb * 3 * a * sizeof(float) + 255) & ~(size_t)255));
+    split_rows_kernel<<<nb, 256, 0, st>>>(w, brand_ids, nb, a, wsplit);
+    dim3 tg((d + 31) / 32, (a + 31) / 32);
+    split_transpose_kernel<<<tg, 256, 0, st>>>(e, a, d, esplit);
+    FRX_LAUNCH_CHECK();
+    return dense_tf32_scaled(wsplit, 3 * (int64_t)a, esplit, 3 * (int64_t)a, nb, d, 3 * a, out_f32, d, 1.0f / (float)a, stream);
+  }
   const bool aligned = (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(e) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0;
   if (a % kFK == 0 && d % 4 == 0 && aligned) {
     dim3 grid((d + kFN - 1) / kFN, (nb + kFM - 1) / kFM);
-    brand_embed_kernel_128<<<grid, 256, 0, (cudaStream_t)stream>>>(w, e, brand_ids, nb, a, d, out_f32);
+    brand_embed_kernel_128<<<grid, 256, 0, st>>>(w, e, brand_ids, nb, a, d, out_f32);
   } else {
     dim3 grid((d + kBN - 1) / kBN, (nb + kBM - 1) / kBM);
-    brand_embed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, e, brand_ids, nb, a, d, out_f32);
+    brand_embed_kernel<<<grid, 256, 0, st>>>(w, e, brand_ids, nb, a, d, out_f32);
   }
   FRX_LAUNCH_CHECK();
   return FRX_OK;

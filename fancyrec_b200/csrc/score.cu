@@ -60,6 +60,7 @@ struct ScoreParams {
   // DENSE
   float* dense;
   int64_t ld_dense;
+  float dense_scale;               // accumulators are multiplied by this before being written (1 = as is)
   // COUNT
   const float* thr_score;
   const int32_t* thr_index;
@@ -398,15 +399,17 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           } else if (MODE == MODE_DENSE) {
             if (row_ok) {
               float* dst = P.dense + (int64_t)row * P.ld_dense + cbase;
+              const float sc = P.dense_scale;
               if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
-                  *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
-                                                                     __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                  *reinterpret_cast<float4*>(dst + i) =
+                      make_float4(__uint_as_float(v[i]) * sc, __uint_as_float(v[i + 1]) * sc,
+                                  __uint_as_float(v[i + 2]) * sc, __uint_as_float(v[i + 3]) * sc);
               } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                  if (i < nvalid) dst[i] = __uint_as_float(v[i]);
+                  if (i < nvalid) dst[i] = __uint_as_float(v[i]) * sc;
               }
             }
           } else {   // MODE_COUNT
@@ -866,7 +869,7 @@ static int check_operands(const char* fn, const void* a, int64_t ld_a, const voi
 
 template <bool TF32>
 static int score_dense_impl(const void* a, int64_t ld_a, const void* b, int64_t ld_b, int nb, int64_t n_posts, int d,
-                            float* dense_out, int64_t ld_dense, void* stream) {
+                            float* dense_out, int64_t ld_dense, void* stream, float scale = 1.0f) {
   int rc = check_operands("frx_score_dense", a, ld_a, b, ld_b, nb, n_posts, d, 0, TF32);
   if (rc) return rc;
   FRX_CHECK_ARG(dense_out && ld_dense >= n_posts, "frx_score_dense: bad output");
@@ -874,6 +877,7 @@ static int score_dense_impl(const void* a, int64_t ld_a, const void* b, int64_t 
   ScoreParams P{};
   P.dense = dense_out;
   P.ld_dense = ld_dense;
+  P.dense_scale = scale;
   return launch_score<MODE_DENSE, TF32>(a, ld_a, b, ld_b, nb, n_posts, d, plan, P, (cudaStream_t)stream);
 }
 
@@ -951,6 +955,7 @@ static int score_topk_impl(const void* a, int64_t ld_a, const void* b, int64_t l
     ScoreParams S{};
     S.dense = sdense;
     S.ld_dense = L.n_s;
+    S.dense_scale = 1.0f;
     rc = launch_score<MODE_DENSE, TF32>(a, ld_a, b, ld_b * L.stride, nb, L.n_s, d, L.sample, S, st, false);
     if (rc) return rc;
     const size_t ksmem = (size_t)L.n_s * sizeof(uint32_t);
@@ -980,6 +985,12 @@ static int score_topk_impl(const void* a, int64_t ld_a, const void* b, int64_t l
   if (rc) return rc;
   if (dense_out) return score_dense_impl<TF32>(a, ld_a, b, ld_b, nb, n_posts, d, dense_out, ld_dense, stream);
   return FRX_OK;
+}
+
+// out[m, n] = scale * sum_k A[m, k] * B[n, k] on the tf32 tensor-core path (used by the 3xTF32 brand embedding).
+int dense_tf32_scaled(const float* a, int64_t ld_a, const float* b, int64_t ld_b, int m, int64_t n, int k, float* out,
+                      int64_t ld_out, float scale, void* stream) {
+  return score_dense_impl<true>(a, ld_a, b, ld_b, m, n, k, out, ld_out, stream, scale);
 }
 
 }  // namespace frx

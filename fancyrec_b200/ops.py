@@ -68,8 +68,9 @@ def finalize_posts(visual, text=None, row_ptr=None, row_idx=None, visual_norm=Fa
     return out_f32, out_bf16
 
 
-def brand_embed(w, e, brand_ids=None, nb=None):
-    """A4: out[i] = mean_a W[ids[i], a] * E[a, :]  -> [nb, D] fp32."""
+def brand_embed(w, e, brand_ids=None, nb=None, tensor_cores=True):
+    """A4: out[i] = mean_a W[ids[i], a] * E[a, :]  -> [nb, D] fp32.  tensor_cores: 3xTF32 tcgen05 GEMM (fp32-grade);
+    False: fp32 FMA GEMM on the CUDA cores."""
     lib = _lib.load()
     _req(w, torch.float32, "w", 2)
     _req(e, torch.float32, "e", 2)
@@ -82,8 +83,11 @@ def brand_embed(w, e, brand_ids=None, nb=None):
     if w.shape[1] != a:
         raise ValueError("w is [*, %d] but e is [%d, *]" % (w.shape[1], a))
     out = torch.empty((nb, d), dtype=torch.float32, device=w.device)
+    need = lib.frx_brand_embed_workspace_bytes(nb, a, d) if tensor_cores else 0
+    ws = torch.empty(need, dtype=torch.uint8, device=w.device) if need else None
     with torch.cuda.device(w.device):
-        rc = lib.frx_brand_embed(_ptr(w), w.shape[0], _ptr(e), _ptr(brand_ids), nb, a, d, _ptr(out), _stream(w))
+        rc = lib.frx_brand_embed(_ptr(w), w.shape[0], _ptr(e), _ptr(brand_ids), nb, a, d, _ptr(out), _ptr(ws), need,
+                                 _stream(w))
     _lib.check(rc, "frx_brand_embed")
     return out
 

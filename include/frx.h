@@ -80,9 +80,14 @@ int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_
  *      out[i, :] = (1/A) * sum_a W[ids[i], a] * E[a, :]
  *   w [w_rows, a] fp32 (nn.Embedding table, brand_num + 1 rows), e [a, d] fp32,
  *   brand_ids [nb] int64 or NULL (= 0 .. nb-1), out_f32 [nb, d].
+ * With a workspace of frx_brand_embed_workspace_bytes (a % 4 == 0) the product runs on the tensor cores as a 3xTF32
+ * GEMM (operands split into tf32 hi + lo parts, K-concatenated, fp32 accumulation: ~1e-6 relative, fp32-grade);
+ * with workspace == NULL it runs as an fp32 FMA GEMM on the CUDA cores.
  */
+size_t frx_brand_embed_workspace_bytes(int nb, int a, int d);
 int frx_brand_embed(const float* w, int64_t w_rows, const float* e, const int64_t* brand_ids,
-                    int nb, int a, int d, float* out_f32, void* stream);
+                    int nb, int a, int d, float* out_f32,
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * A5 + A6  cosine-score contraction with the per-brand top-k fused into the GEMM epilogue.

@@ -83,8 +83,14 @@ def test_brand_embed_matches_oracle_and_golden(golden_dir):
     np.testing.assert_allclose(got, g["brand_emb"], rtol=1e-5, atol=1e-6)
     w2 = synth.gaussian(1, 131, 2000)
     e2 = synth.gaussian(2, 2000, 200)
-    got2 = ops.brand_embed(to_dev(w2), to_dev(e2), nb=130).cpu().numpy()
-    np.testing.assert_allclose(got2, oembed.brand_embed(w2, e2, np.arange(130)), rtol=2e-4, atol=2e-6)
+    want2 = oembed.brand_embed(w2, e2, np.arange(130))
+    for tc in (True, False):      # 3xTF32 tensor-core GEMM and the fp32 CUDA-core GEMM: both fp32-grade
+        got2 = ops.brand_embed(to_dev(w2), to_dev(e2), nb=130, tensor_cores=tc).cpu().numpy()
+        np.testing.assert_allclose(got2, want2, rtol=2e-4, atol=2e-6)
+        assert np.abs(got2 - want2).max() <= 2e-6 * np.abs(want2).max() + 1e-7
+    ids = np.array([5, 5, 130, 0, 77] * 60, dtype=np.int64)
+    got3 = ops.brand_embed(to_dev(w2), to_dev(e2), brand_ids=to_dev(ids)).cpu().numpy()
+    np.testing.assert_allclose(got3, oembed.brand_embed(w2, e2, ids), rtol=2e-4, atol=2e-6)
 
 
 def _fake_model(nb, w, e):
