@@ -834,7 +834,7 @@ static int launch_score(const void* a, int64_t ld_a, const void* b, int64_t ld_b
   P.num_n_tiles = plan.num_n_tiles;
   P.splits = plan.splits;
   FRX_CUDA(cudaFuncSetAttribute(score_kernel<MODE, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  const bool probe = allow_probe && g_probe.on && g_probe.n < 4096;
+  const bool probe = allow_probe && MODE == MODE_TOPK && g_probe.on && g_probe.n < 4096;   // main fused launches only
   const int slot = g_probe.n;
   if (probe) {
     if (!g_probe.made[slot]) {

@@ -216,8 +216,8 @@ int frx_contrastive_fwd_bwd(const float* brand, const float* post, int b, int d,
 int frx_normalize_rows(const float* x, int rows, int d, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Measurement hook (bench.py roofline leg): when enabled, every score kernel launch (top-k, dense,
- * count mode) is bracketed by a pair of CUDA events on its own stream.  frx_probe_read synchronises
+ * Measurement hook (bench.py roofline leg): when enabled, every MAIN launch of the fused score + top-k kernel
+ * (not the sample pass, not dense / count launches) is bracketed by a pair of CUDA events on its own stream.  frx_probe_read synchronises
  * the recorded events and returns up to `max` per-launch durations in milliseconds (oldest first)
  * and clears the log.  Off by default; at most 4096 launches are logged.
  */
