@@ -42,8 +42,15 @@ void set_error(const char* fmt, ...);
 int num_sms();
 
 // score.cu: out[m, n] = scale * sum_k A[m, k] * B[n, k], fp32 operands read as tf32, fp32 accumulation (tcgen05)
+// ksplit_ws (optional): scratch for K-split partial tiles when the output covers only a few tiles
 int dense_tf32_scaled(const float* a, int64_t ld_a, const float* b, int64_t ld_b, int m, int64_t n, int k, float* out,
-                      int64_t ld_out, float scale, void* stream);
+                      int64_t ld_out, float scale, void* stream, void* ksplit_ws = nullptr, size_t ksplit_ws_bytes = 0);
+
+// finalize.cu: 3xTF32 operand preparation.  pattern 0 = [hi | lo | hi] (A side), 1 = [hi | hi | lo] (B side).
+void launch_split_rows(const float* x, const int64_t* ids, int rows, int cols, int64_t ld_x, float scale, int pattern,
+                       float* out, cudaStream_t st);
+void launch_split_transpose(const float* x, int rows, int cols, int64_t ld_x, float scale, int pattern, float* out,
+                            cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // Total order used everywhere: (score descending, post index ascending).

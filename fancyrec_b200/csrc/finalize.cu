@@ -513,40 +513,57 @@ __device__ __forceinline__ float tf32_round(float x) {
   return __uint_as_float(u & 0xFFFFE000u);
 }
 
-// rows of W (gathered through ids) -> [hi | lo | hi]
-__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ w, const int64_t* __restrict__ ids, int nb,
-                                                         int a, float* __restrict__ out) {
+// pattern 0 ("A side"): [hi | lo | hi]     pattern 1 ("B side"): [hi | hi | lo]
+// A'.B'^T over the 3x wide K then equals a_hi.b_hi + a_lo.b_hi + a_hi.b_lo.
+// rows of X (optionally gathered through ids), optionally pre-scaled -> split row of width 3 * cols
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ ids, int cols,
+                                                         int64_t ld_x, float scale, int pattern, float* __restrict__ out) {
   const int r = blockIdx.x;
   const int64_t src = ids ? ids[r] : (int64_t)r;
-  for (int c = threadIdx.x; c < a; c += blockDim.x) {
-    const float x = w[src * a + c];
-    const float hi = tf32_round(x), lo = tf32_round(x - hi);
-    float* o = out + (int64_t)r * 3 * a;
-    o[c] = hi; o[a + c] = lo; o[2 * a + c] = hi;
+  float* o = out + (int64_t)r * 3 * cols;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float v = x[src * ld_x + c] * scale;
+    const float hi = tf32_round(v), lo = tf32_round(v - hi);
+    o[c] = hi;
+    o[cols + c] = pattern ? hi : lo;
+    o[2 * cols + c] = pattern ? lo : hi;
   }
 }
 
-// E [a, d] -> transposed and split: out[n, :] = [E_hi[:, n] | E_hi[:, n] | E_lo[:, n]]   (32x32 smem transpose)
-__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ e, int a, int d, float* __restrict__ out) {
+// X [rows, cols] -> transposed and split: out[n, :] (width 3 * rows) from column n of X   (32x32 smem transpose)
+__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ x, int rows, int cols, int64_t ld_x,
+                                                              float scale, int pattern, float* __restrict__ out) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;    // 32 x 8
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     const int k = k0 + ty + i, n = n0 + tx;
-    tile[ty + i][tx] = (k < a && n < d) ? e[(int64_t)k * d + n] : 0.f;
+    tile[ty + i][tx] = (k < rows && n < cols) ? x[(int64_t)k * ld_x + n] * scale : 0.f;
   }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     const int n = n0 + ty + i, k = k0 + tx;
-    if (n < d && k < a) {
-      const float x = tile[tx][ty + i];
-      const float hi = tf32_round(x), lo = tf32_round(x - hi);
-      float* o = out + (int64_t)n * 3 * a;
-      o[k] = hi; o[a + k] = hi; o[2 * a + k] = lo;
+    if (n < cols && k < rows) {
+      const float v = tile[tx][ty + i];
+      const float hi = tf32_round(v), lo = tf32_round(v - hi);
+      float* o = out + (int64_t)n * 3 * rows;
+      o[k] = hi;
+      o[rows + k] = pattern ? hi : lo;
+      o[2 * rows + k] = pattern ? lo : hi;
     }
   }
+}
+
+void launch_split_rows(const float* x, const int64_t* ids, int rows, int cols, int64_t ld_x, float scale, int pattern,
+                       float* out, cudaStream_t st) {
+  split_rows_kernel<<<rows, 256, 0, st>>>(x, ids, cols, ld_x, scale, pattern, out);
+}
+void launch_split_transpose(const float* x, int rows, int cols, int64_t ld_x, float scale, int pattern, float* out,
+                            cudaStream_t st) {
+  dim3 tg((cols + 31) / 32, (rows + 31) / 32);
+  split_transpose_kernel<<<tg, 256, 0, st>>>(x, rows, cols, ld_x, scale, pattern, out);
 }
 
 static size_t brand_ws_bytes(int nb, int a, int d) {
@@ -626,9 +643,8 @@ int frx_brand_embed(const float* w, int64_t w_rows, const float* e, const int64_
     float* wsplit = reinterpret_cast<float*>(workspace);
     float* esplit = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) +
                                              (((size_t)nb * 3 * a * sizeof(float) + 255) & ~(size_t)255));
-    split_rows_kernel<<<nb, 256, 0, st>>>(w, brand_ids, nb, a, wsplit);
-    dim3 tg((d + 31) / 32, (a + 31) / 32);
-    split_transpose_kernel<<<tg, 256, 0, st>>>(e, a, d, esplit);
+    launch_split_rows(w, brand_ids, nb, a, a, 1.0f, 0, wsplit, st);              // W'   = [W_hi | W_lo | W_hi]
+    launch_split_transpose(e, a, d, d, 1.0f, 1, esplit, st);                     // E'^T = [E_hi | E_hi | E_lo]^T
     FRX_LAUNCH_CHECK();
     return dense_tf32_scaled(wsplit, 3 * (int64_t)a, esplit, 3 * (int64_t)a, nb, d, 3 * a, out_f32, d, 1.0f / (float)a, stream);
   }

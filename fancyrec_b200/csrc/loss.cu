@@ -2,8 +2,8 @@
 // loss_ctrs.py:179-214).  fp32 end to end (the reference computes the tile in fp32); the B x B tile,
 // its rank weights, the hinge / soft-max terms and dS are produced on the device without the B GEMV
 // launches (loss.py:91-93), the four sorts (loss.py:96-105) or the B^2 host loop (loss.py:116-119) of
-// the reference.  Round-1 structure: a register-tiled fp32 GEMM + small fused row kernels; the
-// tensor-core (tf32 tcgen05) tile is the next step.
+// the reference.  The GEMMs (tile, dS.brand, dS^T.post, softmax logits) run on the tensor cores as 3xTF32
+// (fp32-grade) through the same tcgen05 kernel as the scoring path; small fused row kernels do the rest.
 #include "common.cuh"
 
 namespace frx {
@@ -241,17 +241,59 @@ __global__ void __launch_bounds__(256) contrastive_row_kernel(float* __restrict_
   if (threadIdx.x == 0) partial[i] = -logf(expf(dii) / z) * w;
 }
 
-struct TripletWs { float *s, *ds, *rank_p, *rank_b, *diag, *partial; };
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// ---------------------------------------------------------------------------------------------
+// GEMM front-end of the loss tiles.  Tensor-core path: 3xTF32 (operands split into tf32 hi + lo parts by
+// launch_split_*, K-concatenated, ONE tcgen05 tf32 GEMM with fp32 accumulation -> fp32-grade, ~1e-6 relative),
+// with K split over idle SMs when the output is only a few tiles (the B x B tile).  Fallback (odd sizes): the
+// fp32 FMA kernel above.
+//   C[m, n] = alpha * sum_k X[m, k] * Y[n, k]     X given as rows [m, k] (xt = false) or transposed [k, m] (xt = true)
+// ---------------------------------------------------------------------------------------------
+struct TcScratch {
+  float* xa;       // [m, 3k]
+  float* yb;       // [n, 3k]
+  void* ksplit;    // K-split partial tiles
+  size_t ksplit_bytes;
+};
+
+static bool tc_ok(int m, int n, int k) { return k % 4 == 0 && m >= 32 && n >= 32; }
+
+static int gemm_nt(cudaStream_t st, bool tc, const TcScratch& ws, const float* x, bool xt, int64_t ldx, const float* y, bool yt,
+                   int64_t ldy, float* c, int64_t ldc, int m, int n, int k, float alpha) {
+  if (tc) {
+    if (xt) launch_split_transpose(x, k, m, ldx, 1.0f, 0, ws.xa, st); else launch_split_rows(x, nullptr, m, k, ldx, 1.0f, 0, ws.xa, st);
+    if (yt) launch_split_transpose(y, k, n, ldy, 1.0f, 1, ws.yb, st); else launch_split_rows(y, nullptr, n, k, ldy, 1.0f, 1, ws.yb, st);
+    return dense_tf32_scaled(ws.xa, 3 * (int64_t)k, ws.yb, 3 * (int64_t)k, m, n, 3 * k, c, ldc, alpha, st, ws.ksplit,
+                             ws.ksplit_bytes);
+  }
+  // X(m,k): rows -> (ldx, 1), transposed -> (1, ldx);   Y as B(k,n): rows [n,k] -> (sbk=1, sbn=ldy), transposed [k,n] -> (ldy, 1)
+  sgemm(st, x, xt ? 1 : ldx, xt ? ldx : 1, y, yt ? ldy : 1, yt ? 1 : ldy, c, ldc, m, n, k, alpha, 0.f);
+  return FRX_OK;
+}
+
+// scratch of one loss op with batch b, width d and nk key rows (nk = b without a queue):
+//   xa: split A operand, at most [b, 3 * max(d, nk)]      yb: split B operand, at most 3 * d * max(b, nk) floats
+//   ks: K-split partial tiles of the B x B GEMMs (32 splits worth)
+static size_t xa_bytes(int b, int d, int nk) { return align256((size_t)b * 3 * (size_t)(d > nk ? d : nk) * sizeof(float)); }
+static size_t yb_bytes(int b, int d, int nk) { return align256((size_t)3 * d * (size_t)(b > nk ? b : nk) * sizeof(float)); }
+static size_t ks_bytes(int b) { return align256((size_t)b * b * sizeof(float) * 32); }
+static size_t tc_scratch_bytes(int b, int d, int nk) { return xa_bytes(b, d, nk) + yb_bytes(b, d, nk) + ks_bytes(b); }
+
+// out = a + b (+ c), elementwise (gradient accumulation of separately computed GEMMs)
+__global__ void add3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, int64_t n,
+                            float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = a[i] + b[i] + (c ? c[i] : 0.f);
+}
 
 }  // namespace frx
 
 extern "C" {
 
 size_t frx_triplet_workspace_bytes(int b, int d) {
-  (void)d;
-  if (b <= 0) return 0;
-  return 2 * frx::align256((size_t)b * b * 4) + 4 * frx::align256((size_t)b * 4) + 256;
+  if (b <= 0 || d <= 0) return 0;
+  return 2 * frx::align256((size_t)b * b * 4) + 4 * frx::align256((size_t)b * 4) + frx::tc_scratch_bytes(b, d, b) + 256;
 }
 
 int frx_triplet_fwd_bwd(const int64_t* brand_ids, const float* brand, const float* post, int b, int d, float margin,
@@ -272,16 +314,25 @@ int frx_triplet_fwd_bwd(const int64_t* brand_ids, const float* brand, const floa
   float* rank_p = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
   float* rank_b = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
   float* diag = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
-  float* partial = reinterpret_cast<float*>(w);
+  float* partial = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
+  TcScratch ts;
+  ts.xa = reinterpret_cast<float*>(w); w += xa_bytes(b, d, b);
+  ts.yb = reinterpret_cast<float*>(w); w += yb_bytes(b, d, b);
+  ts.ksplit = w;
+  ts.ksplit_bytes = ks_bytes(b);
+  const bool tc = tc_ok(b, b, d) && b % 4 == 0;
   const float scale = mean_style ? 1.0f / ((float)b * (float)b) : 1.0f;
   // S[i,j] = post_i . brand_j   (loss.py:91-93)
-  sgemm(st, post, d, 1, brand, 1, d, s, b, b, b, d, 1.f, 0.f);
+  int rc = gemm_nt(st, tc, ts, post, false, d, brand, false, d, s, b, b, b, d, 1.f);
+  if (rc) return rc;
   tile_rank_kernel<<<b, 128, 0, st>>>(s, b, rank_p, rank_b, diag);
   triplet_row_kernel<<<b, 256, 0, st>>>(s, brand_ids, b, margin, scale, rank_p, rank_b, diag, ds, partial);
   reduce_partials_kernel<<<1, 256, 0, st>>>(partial, b, scale, loss);
   if (d_post) {
-    sgemm(st, ds, b, 1, brand, d, 1, d_post, d, b, d, b, 1.f, 0.f);     // dPost  = dS   . brand
-    sgemm(st, ds, 1, b, post, d, 1, d_brand, d, b, d, b, 1.f, 0.f);     // dBrand = dS^T . post
+    rc = gemm_nt(st, tc, ts, ds, false, b, brand, true, d, d_post, d, b, d, b, 1.f);     // dPost  = dS   . brand
+    if (rc) return rc;
+    rc = gemm_nt(st, tc, ts, ds, true, b, post, true, d, d_brand, d, b, d, b, 1.f);      // dBrand = dS^T . post
+    if (rc) return rc;
   }
   FRX_LAUNCH_CHECK();
   return FRX_OK;
@@ -290,8 +341,8 @@ int frx_triplet_fwd_bwd(const int64_t* brand_ids, const float* brand, const floa
 size_t frx_contrastive_workspace_bytes(int b, int d, int n_keys) {
   if (b <= 0 || d <= 0) return 0;
   const int nk = n_keys > 0 ? n_keys : b;
-  return frx::align256((size_t)b * b * 4) + frx::align256((size_t)b * nk * 4) + 4 * frx::align256((size_t)b * d * 4) +
-         6 * frx::align256((size_t)b * 4) + 256;
+  return frx::align256((size_t)b * b * 4) + frx::align256((size_t)b * nk * 4) + 7 * frx::align256((size_t)b * d * 4) +
+         6 * frx::align256((size_t)b * 4) + frx::tc_scratch_bytes(b, d, nk) + 256;
 }
 
 int frx_contrastive_fwd_bwd(const float* brand, const float* post, int b, int d, const float* keys, int n_keys,
@@ -319,35 +370,63 @@ int frx_contrastive_fwd_bwd(const float* brand, const float* post, int b, int d,
   float* pn = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
   float* dbn = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
   float* dpn = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
+  float* t1 = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
+  float* t2 = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
+  float* t3 = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
   float* weight = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
   float* rank_b = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
   float* diag = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
   float* partial = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
   float* nrm_b = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
-  float* nrm_p = reinterpret_cast<float*>(w);
+  float* nrm_p = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
+  TcScratch ts;
+  ts.xa = reinterpret_cast<float*>(w); w += xa_bytes(b, d, nk);
+  ts.yb = reinterpret_cast<float*>(w); w += yb_bytes(b, d, nk);
+  ts.ksplit = w;
+  ts.ksplit_bytes = ks_bytes(b);
+  const bool tc = tc_ok(b, b, d) && b % 4 == 0 && nk % 4 == 0;
   const float inv_t = 1.0f / temperature;
   const float scale = mean_style ? 1.0f / (float)b : 1.0f;
   // rank weight from the RAW tile (loss_ctrs.py:182-192)
-  sgemm(st, post, d, 1, brand, 1, d, inter, b, b, b, d, 1.f, 0.f);
+  int rc = gemm_nt(st, tc, ts, post, false, d, brand, false, d, inter, b, b, b, d, 1.f);
+  if (rc) return rc;
   tile_rank_kernel<<<b, 128, 0, st>>>(inter, b, weight, rank_b, diag);
   normalize_rows_kernel<<<b, 256, 0, st>>>(brand, d, bn, nrm_b);
   normalize_rows_kernel<<<b, 256, 0, st>>>(post, d, pn, nrm_p);
   const float* kk = keys ? keys : pn;
   // inter[i,j] = bn_i . pn_j / T ; ori[i,q] = pn_i . key_q
-  sgemm(st, bn, d, 1, pn, 1, d, inter, b, b, b, d, inv_t, 0.f);
-  sgemm(st, pn, d, 1, kk, 1, d, ori, nk, b, nk, d, 1.f, 0.f);
+  rc = gemm_nt(st, tc, ts, bn, false, d, pn, false, d, inter, b, b, b, d, inv_t);
+  if (rc) return rc;
+  rc = gemm_nt(st, tc, ts, pn, false, d, kk, false, d, ori, nk, b, nk, d, 1.f);
+  if (rc) return rc;
   contrastive_row_kernel<<<b, 256, 0, st>>>(inter, ori, b, nk, mask_col0, no_intra, inv_t, negative_weight, scale,
                                             weight, partial);
   reduce_partials_kernel<<<1, 256, 0, st>>>(partial, b, scale, loss);
   if (d_post) {
-    sgemm(st, inter, b, 1, pn, d, 1, dbn, d, b, d, b, inv_t, 0.f);       // d_bn  = dInter   . pn / T
-    sgemm(st, inter, 1, b, bn, d, 1, dpn, d, b, d, b, inv_t, 0.f);       // d_pn  = dInter^T . bn / T
+    rc = gemm_nt(st, tc, ts, inter, false, b, pn, true, d, dbn, d, b, d, b, inv_t);        // d_bn = dInter   . pn / T
+    if (rc) return rc;
+    rc = gemm_nt(st, tc, ts, inter, true, b, bn, true, d, t1, d, b, d, b, inv_t);          // t1   = dInter^T . bn / T
+    if (rc) return rc;
+    const float* sum2 = nullptr;
+    const float* sum3 = nullptr;
     if (!no_intra) {
-      sgemm(st, ori, nk, 1, kk, d, 1, dpn, d, b, d, nk, 1.f, 1.f);       //       + G . keys
-      if (!keys) sgemm(st, ori, 1, nk, pn, d, 1, dpn, d, b, d, b, 1.f, 1.f);   // + G^T . pn (keys = pn carry grad)
+      rc = gemm_nt(st, tc, ts, ori, false, nk, kk, true, d, t2, d, b, d, nk, 1.f);         // t2 = G . keys
+      if (rc) return rc;
+      sum2 = t2;
+      if (!keys) {                                                                         // keys = pn carry grad too
+        rc = gemm_nt(st, tc, ts, ori, true, nk, pn, true, d, t3, d, b, d, b, 1.f);         // t3 = G^T . pn
+        if (rc) return rc;
+        sum3 = t3;
+      }
+    }
+    const float* dpn_src = t1;
+    if (sum2) {
+      const int64_t n = (int64_t)b * d;
+      add3_kernel<<<(int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>(t1, sum2, sum3, n, dpn);
+      dpn_src = dpn;
     }
     normalize_bwd_kernel<<<b, 256, 0, st>>>(dbn, bn, nrm_b, d, d_brand);
-    normalize_bwd_kernel<<<b, 256, 0, st>>>(dpn, pn, nrm_p, d, d_post);
+    normalize_bwd_kernel<<<b, 256, 0, st>>>(dpn_src, pn, nrm_p, d, d_post);
   }
   FRX_LAUNCH_CHECK();
   return FRX_OK;

@@ -48,6 +48,8 @@ struct ScoreParams {
   int nb;
   int64_t n_posts;
   int num_k_blocks, num_m_tiles, splits;
+  int k_splits;                    // DENSE only: K range split over work items, partial tiles reduced afterwards
+  int64_t partial_stride;          // elements between the partial tiles of consecutive k-splits
   int64_t num_n_tiles;
   int64_t index_base;
   // TOPK
@@ -223,17 +225,19 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
 
-  const int n_items = P.num_m_tiles * P.splits;
+  const int n_items = P.num_m_tiles * P.splits * P.k_splits;      // item = (split * num_m_tiles + m_tile) * k_splits + ks
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int m_tile = item % P.num_m_tiles, split = item / P.num_m_tiles;
+        const int ks = item % P.k_splits, mi = item / P.k_splits;
+        const int m_tile = mi % P.num_m_tiles, split = mi / P.num_m_tiles;
+        const int kb0 = P.num_k_blocks * ks / P.k_splits, kb1 = P.num_k_blocks * (ks + 1) / P.k_splits;
         const int64_t t0 = P.num_n_tiles * split / P.splits, t1 = P.num_n_tiles * (split + 1) / P.splits;
         for (int64_t t = t0; t < t1; ++t) {
-          for (int kb = 0; kb < P.num_k_blocks; ++kb) {
+          for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(smem_u32(&tail->empty[stage]), phase ^ 1);
             const uint32_t fb = smem_u32(&tail->full[stage]);
             mbar_arrive_expect_tx(fb, STAGE_BYTES);
@@ -251,13 +255,14 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int split = item / P.num_m_tiles;
+        const int ks = item % P.k_splits, split = (item / P.k_splits) / P.num_m_tiles;
+        const int kb0 = P.num_k_blocks * ks / P.k_splits, kb1 = P.num_k_blocks * (ks + 1) / P.k_splits;
         const int64_t t0 = P.num_n_tiles * split / P.splits, t1 = P.num_n_tiles * (split + 1) / P.splits;
         for (int64_t t = t0; t < t1; ++t) {
           mbar_wait(smem_u32(&tail->tmem_empty[as]), aphase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * BN;
-          for (int kb = 0; kb < P.num_k_blocks; ++kb) {
+          for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(smem_u32(&tail->full[stage]), phase);
             tc_fence_after();
             const uint64_t da = make_sw128_kmajor_desc(smem_a + stage * A_STAGE_BYTES);
@@ -265,11 +270,11 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < MMAS_PER_KBLOCK; ++k) {
               // advance 16 bf16 / 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
-              if (TF32) umma_tf32_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-              else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              if (TF32) umma_tf32_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0));
+              else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0));
             }
             umma_commit(smem_u32(&tail->empty[stage]));        // frees the smem slot when the MMAs retire
-            if (kb == P.num_k_blocks - 1) umma_commit(smem_u32(&tail->tmem_full[as]));
+            if (kb == kb1 - 1) umma_commit(smem_u32(&tail->tmem_full[as]));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           if (++as == 2) { as = 0; aphase ^= 1; }
@@ -287,7 +292,8 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     uint32_t* hist = tail->hist[ew];
     int as = 0; uint32_t aphase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int m_tile = item % P.num_m_tiles, split = item / P.num_m_tiles;
+      const int ks = item % P.k_splits, mi = item / P.k_splits;
+      const int m_tile = mi % P.num_m_tiles, split = mi / P.num_m_tiles;
       const int64_t t0 = P.num_n_tiles * split / P.splits, t1 = P.num_n_tiles * (split + 1) / P.splits;
       const int row = m_tile * BM + row_in_tile;
       const bool row_ok = row < P.nb;
@@ -398,7 +404,7 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             }
           } else if (MODE == MODE_DENSE) {
             if (row_ok) {
-              float* dst = P.dense + (int64_t)row * P.ld_dense + cbase;
+              float* dst = P.dense + (int64_t)ks * P.partial_stride + (int64_t)row * P.ld_dense + cbase;
               const float sc = P.dense_scale;
               if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
@@ -833,6 +839,7 @@ static int launch_score(const void* a, int64_t ld_a, const void* b, int64_t ld_b
   P.num_m_tiles = plan.num_m_tiles;
   P.num_n_tiles = plan.num_n_tiles;
   P.splits = plan.splits;
+  if (P.k_splits < 1) P.k_splits = 1;
   FRX_CUDA(cudaFuncSetAttribute(score_kernel<MODE, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   const bool probe = allow_probe && MODE == MODE_TOPK && g_probe.on && g_probe.n < 4096;   // main fused launches only
   const int slot = g_probe.n;
@@ -844,7 +851,9 @@ static int launch_score(const void* a, int64_t ld_a, const void* b, int64_t ld_b
     }
     FRX_CUDA(cudaEventRecord(g_probe.beg[slot], st));
   }
-  score_kernel<MODE, TF32><<<plan.grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
+  long total_items = (long)plan.num_m_tiles * plan.splits * P.k_splits;
+  const int grid = (int)(total_items < num_sms() ? total_items : num_sms());
+  score_kernel<MODE, TF32><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
   FRX_LAUNCH_CHECK();
   if (probe) {
     FRX_CUDA(cudaEventRecord(g_probe.end[slot], st));
@@ -867,18 +876,61 @@ static int check_operands(const char* fn, const void* a, int64_t ld_a, const voi
   return frx_device_check(dev);
 }
 
+// out[i] = scale * sum_ks partial[ks][i], summed in k-split order (deterministic)
+__global__ void reduce_ksplit_kernel(const float* __restrict__ partial, int64_t stride, int k_splits, int64_t rows,
+                                     int64_t cols, int64_t ld_partial, float* __restrict__ out, int64_t ld_out, float scale) {
+  const int64_t n = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i % cols;
+    float acc = 0.f;
+    for (int ks = 0; ks < k_splits; ++ks) acc += partial[(int64_t)ks * stride + r * ld_partial + c];
+    out[r * ld_out + c] = acc * scale;
+  }
+}
+
 template <bool TF32>
 static int score_dense_impl(const void* a, int64_t ld_a, const void* b, int64_t ld_b, int nb, int64_t n_posts, int d,
-                            float* dense_out, int64_t ld_dense, void* stream, float scale = 1.0f) {
+                            float* dense_out, int64_t ld_dense, void* stream, float scale = 1.0f,
+                            void* ksplit_ws = nullptr, size_t ksplit_ws_bytes = 0) {
   int rc = check_operands("frx_score_dense", a, ld_a, b, ld_b, nb, n_posts, d, 0, TF32);
   if (rc) return rc;
   FRX_CHECK_ARG(dense_out && ld_dense >= n_posts, "frx_score_dense: bad output");
   Plan plan = make_plan(nb, n_posts, 1, MODE_DENSE);
   ScoreParams P{};
-  P.dense = dense_out;
   P.ld_dense = ld_dense;
-  P.dense_scale = scale;
-  return launch_score<MODE_DENSE, TF32>(a, ld_a, b, ld_b, nb, n_posts, d, plan, P, (cudaStream_t)stream);
+  // Small outputs (the B x B loss tile) cover only a few tiles: split K over the idle SMs and reduce afterwards.
+  const int sms = num_sms();
+  const long tile_units = (long)plan.num_m_tiles * plan.num_n_tiles;
+  const int nkb = (d + (TF32 ? 32 : 64) - 1) / (TF32 ? 32 : 64);
+  int k_splits = 1;
+  if (ksplit_ws != nullptr && tile_units * 2 <= sms) {
+    k_splits = (int)(sms / tile_units);
+    if (k_splits > nkb / 4) k_splits = nkb / 4;                 // at least 4 k-blocks per item
+    const size_t per_split = (size_t)nb * (size_t)n_posts * sizeof(float);
+    if (per_split > 0 && (size_t)k_splits > ksplit_ws_bytes / per_split) k_splits = (int)(ksplit_ws_bytes / per_split);
+    if (k_splits < 1) k_splits = 1;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k_splits == 1) {
+    P.dense = dense_out;
+    P.dense_scale = scale;
+    return launch_score<MODE_DENSE, TF32>(a, ld_a, b, ld_b, nb, n_posts, d, plan, P, st);
+  }
+  plan.splits = (int)plan.num_n_tiles;                          // one n-tile per item, K split k_splits ways
+  P.dense = reinterpret_cast<float*>(ksplit_ws);
+  P.ld_dense = n_posts;
+  P.partial_stride = (int64_t)nb * n_posts;
+  P.k_splits = k_splits;
+  P.dense_scale = 1.0f;
+  rc = launch_score<MODE_DENSE, TF32>(a, ld_a, b, ld_b, nb, n_posts, d, plan, P, st);
+  if (rc) return rc;
+  const int64_t n = (int64_t)nb * n_posts;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+  reduce_ksplit_kernel<<<(int)blocks, 256, 0, st>>>(P.dense, P.partial_stride, k_splits, nb, n_posts, n_posts, dense_out,
+                                                    ld_dense, scale);
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
 }
 
 template <bool TF32>
@@ -989,8 +1041,8 @@ static int score_topk_impl(const void* a, int64_t ld_a, const void* b, int64_t l
 
 // out[m, n] = scale * sum_k A[m, k] * B[n, k] on the tf32 tensor-core path (used by the 3xTF32 brand embedding).
 int dense_tf32_scaled(const float* a, int64_t ld_a, const float* b, int64_t ld_b, int m, int64_t n, int k, float* out,
-                      int64_t ld_out, float scale, void* stream) {
-  return score_dense_impl<true>(a, ld_a, b, ld_b, m, n, k, out, ld_out, stream, scale);
+                      int64_t ld_out, float scale, void* stream, void* ksplit_ws, size_t ksplit_ws_bytes) {
+  return score_dense_impl<true>(a, ld_a, b, ld_b, m, n, k, out, ld_out, stream, scale, ksplit_ws, ksplit_ws_bytes);
 }
 
 }  // namespace frx
