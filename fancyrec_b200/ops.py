@@ -109,13 +109,13 @@ def _variant(lib, name, post_op):
     return getattr(lib, name + ("_tf32" if post_op.dtype == torch.float32 else ""))
 
 
-def score_topk(brand_bf16, post_bf16, k, d=None, labels=None, index_base=0, workspace=None, dense=False):
+def score_topk(brand_op, post_op, k, d=None, labels=None, index_base=0, workspace=None, dense=False):
     """A5+A6 fused.  Returns dict(scores [NB,k] f32, index [NB,k] i32, pos_score [NP] f32 | None,
     dense [NB,NP] f32 | None)."""
     lib = _lib.load()
-    d = _operands(brand_bf16, post_bf16, d)
-    nb, n_posts = brand_bf16.shape[0], post_bf16.shape[0]
-    dev = post_bf16.device
+    d = _operands(brand_op, post_op, d)
+    nb, n_posts = brand_op.shape[0], post_op.shape[0]
+    dev = post_op.device
     need = lib.frx_score_topk_workspace_bytes(nb, n_posts, d, k)
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -127,39 +127,39 @@ def score_topk(brand_bf16, post_bf16, k, d=None, labels=None, index_base=0, work
         pos_score = torch.empty(n_posts, dtype=torch.float32, device=dev)
     dense_out = torch.empty((nb, n_posts), dtype=torch.float32, device=dev) if dense else None
     with torch.cuda.device(dev):
-        rc = _variant(lib, "frx_score_topk", post_bf16)(_ptr(brand_bf16), brand_bf16.stride(0), _ptr(post_bf16), post_bf16.stride(0), nb,
+        rc = _variant(lib, "frx_score_topk", post_op)(_ptr(brand_op), brand_op.stride(0), _ptr(post_op), post_op.stride(0), nb,
                                 n_posts, d, k, _ptr(labels), index_base, _ptr(scores), _ptr(index), _ptr(pos_score),
-                                _ptr(dense_out), n_posts, _ptr(workspace), workspace.numel(), _stream(post_bf16))
+                                _ptr(dense_out), n_posts, _ptr(workspace), workspace.numel(), _stream(post_op))
     _lib.check(rc, "frx_score_topk")
     return dict(scores=scores, index=index, pos_score=pos_score, dense=dense_out, workspace=workspace)
 
 
-def score_dense(brand_bf16, post_bf16, d=None, out=None):
+def score_dense(brand_op, post_op, d=None, out=None):
     lib = _lib.load()
-    d = _operands(brand_bf16, post_bf16, d)
-    nb, n_posts = brand_bf16.shape[0], post_bf16.shape[0]
+    d = _operands(brand_op, post_op, d)
+    nb, n_posts = brand_op.shape[0], post_op.shape[0]
     if out is None:
-        out = torch.empty((nb, n_posts), dtype=torch.float32, device=post_bf16.device)
-    with torch.cuda.device(post_bf16.device):
-        rc = _variant(lib, "frx_score_dense", post_bf16)(_ptr(brand_bf16), brand_bf16.stride(0), _ptr(post_bf16), post_bf16.stride(0), nb,
-                                 n_posts, d, _ptr(out), out.stride(0), _stream(post_bf16))
+        out = torch.empty((nb, n_posts), dtype=torch.float32, device=post_op.device)
+    with torch.cuda.device(post_op.device):
+        rc = _variant(lib, "frx_score_dense", post_op)(_ptr(brand_op), brand_op.stride(0), _ptr(post_op), post_op.stride(0), nb,
+                                 n_posts, d, _ptr(out), out.stride(0), _stream(post_op))
     _lib.check(rc, "frx_score_dense")
     return out
 
 
-def score_count(brand_bf16, post_bf16, thr_score, thr_index, d=None, index_base=0, out=None):
+def score_count(brand_op, post_op, thr_score, thr_index, d=None, index_base=0, out=None):
     """Per brand: number of posts preceding (thr_score, thr_index).  Accumulates into ``out`` (int64)."""
     lib = _lib.load()
-    d = _operands(brand_bf16, post_bf16, d)
-    nb, n_posts = brand_bf16.shape[0], post_bf16.shape[0]
+    d = _operands(brand_op, post_op, d)
+    nb, n_posts = brand_op.shape[0], post_op.shape[0]
     _req(thr_score, torch.float32, "thr_score", 1)
     _req(thr_index, torch.int32, "thr_index", 1)
     if out is None:
-        out = torch.zeros(nb, dtype=torch.int64, device=post_bf16.device)
-    with torch.cuda.device(post_bf16.device):
-        rc = _variant(lib, "frx_score_count", post_bf16)(_ptr(brand_bf16), brand_bf16.stride(0), _ptr(post_bf16), post_bf16.stride(0), nb,
+        out = torch.zeros(nb, dtype=torch.int64, device=post_op.device)
+    with torch.cuda.device(post_op.device):
+        rc = _variant(lib, "frx_score_count", post_op)(_ptr(brand_op), brand_op.stride(0), _ptr(post_op), post_op.stride(0), nb,
                                  n_posts, d, index_base, _ptr(thr_score), _ptr(thr_index), _ptr(out),
-                                 _stream(post_bf16))
+                                 _stream(post_op))
     _lib.check(rc, "frx_score_count")
     return out
 

@@ -212,3 +212,31 @@ def test_encode_data_contract():
     brands, embs = evaluator.encode_data(_Model(), _Loader(), log_step=1, logging=logs.append)
     assert torch.equal(embs.cpu(), data) and embs.is_cuda
     assert brands.cpu().tolist() == [0, 1, 2, 0, 0, 2, 1, 1, 0, 2] and len(logs) == 3
+
+
+def test_bigfile_ingest_to_device(tmp_path):
+    """feature.bin -> ImageBigFile.read_csr -> ONE finalize pass on the device == the reference's per-frame
+    read_one + torch.mean + l2norm path (util/imgbigfile.py:19-57, util/data_provider.py:40, evaluator.py:14-19)."""
+    from fancyrec_b200 import ops
+    from fancyrec_b200.util.imgbigfile import ImageBigFile
+    rs = np.random.RandomState(17)
+    n_rows, dims = 300, 128
+    feats = np.maximum(rs.standard_normal((n_rows, dims)), 0).astype(np.float32)
+    names = ["v%d_frame_%d_cls%d" % (i // 7, i % 7, i % 5) for i in range(n_rows)]
+    perm = rs.permutation(n_rows)                          # frames of one video are scattered in the file
+    feats_file, names_file = feats[perm], [names[i] for i in perm]
+    feats_file.tofile(os.path.join(str(tmp_path), "feature.bin"))
+    open(os.path.join(str(tmp_path), "id.txt"), "w", encoding="utf8").write("#".join(names_file))
+    open(os.path.join(str(tmp_path), "shape.txt"), "w").write("%d %d" % (n_rows, dims))
+    bf = ImageBigFile(str(tmp_path))
+    posts = [[n for n in names if n.startswith("v%d_" % v)] for v in range(n_rows // 7 + 1)]
+    posts = [p for p in posts if p]
+    row_idx, row_ptr = bf.read_csr(posts)
+    out = ops.finalize_posts(to_dev(np.asarray(bf.matrix)), row_ptr=to_dev(row_ptr), row_idx=to_dev(row_idx),
+                             final_norm=True, want_f32=True, want_bf16=False)[0].cpu().numpy()
+    want = []
+    for frames in posts:                                   # the reference way, frame by frame
+        vecs = np.array([bf.read_one(f) for f in frames], dtype=np.float32)
+        m = vecs.astype(np.float64).mean(0)
+        want.append(m / np.sqrt((m * m).sum()))
+    np.testing.assert_allclose(out, np.array(want), rtol=RTOL, atol=1e-7)
