@@ -67,6 +67,7 @@ struct ScoreParams {
   const float* thr_score;
   const int32_t* thr_index;
   unsigned long long* count_out;
+  long long* trace;                // FRX_TRACE builds only: per-tile clock64 stamps of CTA 0 (4 per tile)
 };
 
 struct SmemTail {
@@ -261,6 +262,9 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         for (int64_t t = t0; t < t1; ++t) {
           mbar_wait(smem_u32(&tail->tmem_empty[as]), aphase ^ 1);
           tc_fence_after();
+#ifdef FRX_TRACE
+          if (P.trace && blockIdx.x == 0 && (t - t0) < 256) P.trace[(t - t0) * 4 + 0] = clock64();
+#endif
           const uint32_t d_tmem = tmem_base + as * BN;
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(smem_u32(&tail->full[stage]), phase);
@@ -274,7 +278,12 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
               else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0));
             }
             umma_commit(smem_u32(&tail->empty[stage]));        // frees the smem slot when the MMAs retire
-            if (kb == kb1 - 1) umma_commit(smem_u32(&tail->tmem_full[as]));
+            if (kb == kb1 - 1) {
+              umma_commit(smem_u32(&tail->tmem_full[as]));
+#ifdef FRX_TRACE
+              if (P.trace && blockIdx.x == 0 && (t - t0) < 256) P.trace[(t - t0) * 4 + 1] = clock64();
+#endif
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           if (++as == 2) { as = 0; aphase ^= 1; }
@@ -324,6 +333,9 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         }
         mbar_wait(smem_u32(&tail->tmem_full[as]), aphase);
         tc_fence_after();
+#ifdef FRX_TRACE
+        if (P.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && (t - t0) < 256) P.trace[(t - t0) * 4 + 2] = clock64();
+#endif
 #pragma unroll 1
         for (int c = 0; c < CHUNKS; ++c) {
           uint32_t v[32];
@@ -435,6 +447,9 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         // release this accumulator stage to the MMA warp
         tc_fence_before();
         __syncwarp();
+#ifdef FRX_TRACE
+        if (P.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && (t - t0) < 256) P.trace[(t - t0) * 4 + 3] = clock64();
+#endif
         if (lane == 0) mbar_arrive(smem_u32(&tail->tmem_empty[as]));
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
@@ -775,6 +790,10 @@ static Plan make_plan(int nb, int64_t n_posts, int k, int mode) {
 }
 
 // ---- measurement hook: CUDA events around each score_kernel launch --------------------------
+#ifdef FRX_TRACE
+static long long* g_trace = nullptr;     // debug builds only (tools/gpu_trace_pipeline.py)
+#endif
+
 struct Probe {
   bool on = false;
   int n = 0;
@@ -840,6 +859,9 @@ static int launch_score(const void* a, int64_t ld_a, const void* b, int64_t ld_b
   P.num_n_tiles = plan.num_n_tiles;
   P.splits = plan.splits;
   if (P.k_splits < 1) P.k_splits = 1;
+#ifdef FRX_TRACE
+  P.trace = (MODE == MODE_TOPK && allow_probe) ? g_trace : nullptr;
+#endif
   FRX_CUDA(cudaFuncSetAttribute(score_kernel<MODE, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   const bool probe = allow_probe && MODE == MODE_TOPK && g_probe.on && g_probe.n < 4096;   // main fused launches only
   const int slot = g_probe.n;
@@ -1091,6 +1113,10 @@ int frx_score_count_tf32(const float* brand_f32, int64_t ld_a, const float* post
   return frx::score_count_impl<true>(brand_f32, ld_a, post_f32, ld_b, nb, n_posts, d, index_base, thr_score, thr_index,
                                      count_out, stream);
 }
+
+#ifdef FRX_TRACE
+int frx_debug_set_trace(long long* device_buf) { frx::g_trace = device_buf; return 0; }
+#endif
 
 int frx_probe_enable(int on) {
   frx::g_probe.on = on != 0;

@@ -87,9 +87,9 @@ def host_statistics(dev_stats, n_posts, want_auc=True):
     n_pos, first_in_list, before, valid, mask = packed[0], packed[1], packed[2], packed[3] != 0, packed[4]
     first_rank = np.where(valid, before, first_in_list)
     first_rank = np.where(n_pos > 0, first_rank, -1)
-    mask = np.ascontiguousarray(mask).view(np.uint64)
     depth = min(HIT_DEPTH, n_posts)
-    hits = ((mask[:, None] >> np.arange(depth, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(np.uint8)
+    # bit r of the 64-bit mask = relevance of rank r: unpack little-endian bytes, keep the first `depth` ranks
+    hits = np.unpackbits(np.ascontiguousarray(mask).view(np.uint8).reshape(-1, 8), axis=1, bitorder='little')[:, :depth]
     st = dict(n_pos=n_pos.copy(), first_rank=first_rank, hits=hits)
     if want_auc:
         st["auc_num"] = packed[5].copy()
