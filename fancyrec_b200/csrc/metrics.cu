@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(256) sort_segments_kernel(const int64_t* __res
 
 // ---- exact AUC numerator + "posts before the first positive" from dense score rows ---------
 constexpr int kAucChunk = 8192;   // positives staged in shared memory per sweep (32 KB)
+constexpr int kAucBuckets = 1024; // coarse score -> first-guess index table (exactness comes from the fix-up scan)
 
 __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__ scores, int64_t ld, int row0,
                                                        int64_t n_posts, const int32_t* __restrict__ labels,
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__
                                                        unsigned long long* __restrict__ auc_num,
                                                        unsigned long long* __restrict__ before_first) {
   __shared__ float spos[kAucChunk];
+  __shared__ int guess[kAucBuckets + 1];
   __shared__ unsigned long long red[2][8];
   const int r = blockIdx.x;
   const int b = row0 + r;
@@ -175,17 +177,42 @@ __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__
     __syncthreads();
     for (int i = threadIdx.x; i < m; i += blockDim.x) spos[i] = pos_sorted[p0 + ch + i];
     __syncthreads();
+    // guess[q] = upper_bound(spos, lower edge of bucket q): a negative score s in bucket q has its exact
+    // upper_bound at or after guess[q]; the scan below fixes the guess up in both directions, so the bucket
+    // arithmetic never affects the result, only the number of steps (typically 0-2 instead of log2(m)).
+    const float lo_s = spos[0], hi_s = spos[m - 1];
+    const float inv_w = (hi_s > lo_s) ? (float)kAucBuckets / (hi_s - lo_s) : 0.f;
+    for (int q = threadIdx.x; q <= kAucBuckets; q += blockDim.x) {
+      const float edge = lo_s + (float)q / inv_w;
+      int lo = 0, hi = m;
+      if (inv_w > 0.f) {
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (spos[mid] > edge) hi = mid; else lo = mid + 1; }
+      }
+      guess[q] = inv_w > 0.f ? lo : 0;
+    }
+    __syncthreads();
     for (int64_t j = c0 + threadIdx.x; j < c1; j += blockDim.x) {
       const float s = row[j];
       if (ch == 0) before += ((s > bs) || (s == bs && (index_base + j) < bi)) ? 1ull : 0ull;
       if (labels[j] == b) continue;          // negatives only (evaluator.py:112)
       // number of positives e in this chunk with e > s  ==  m - upper_bound(spos, s)
-      int lo = 0, hi = m;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (spos[mid] > s) hi = mid; else lo = mid + 1;
+      int idx;
+      if (!(s >= lo_s)) idx = 0;             // below every positive (or NaN)
+      else if (s >= hi_s) idx = m;           // at or above every positive
+      else {
+        int q = (int)((s - lo_s) * inv_w);
+        q = q < 0 ? 0 : (q > kAucBuckets ? kAucBuckets : q);
+        idx = guess[q];
+        int steps = 0;
+        while (idx < m && spos[idx] <= s && steps < 8) { ++idx; ++steps; }
+        while (idx > 0 && spos[idx - 1] > s && steps < 8) { --idx; ++steps; }
+        if (steps >= 8) {                      // crowded bucket (ties / clustered positives): exact binary search
+          int lo = 0, hi = m;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (spos[mid] > s) hi = mid; else lo = mid + 1; }
+          idx = lo;
+        }
       }
-      auc += (unsigned long long)(m - lo);
+      auc += (unsigned long long)(m - idx);
     }
   }
   // block reduce

@@ -232,7 +232,7 @@ def test_bigfile_ingest_to_device(tmp_path):
     posts = [[n for n in names if n.startswith("v%d_" % v)] for v in range(n_rows // 7 + 1)]
     posts = [p for p in posts if p]
     row_idx, row_ptr = bf.read_csr(posts)
-    out = ops.finalize_posts(to_dev(np.asarray(bf.matrix)), row_ptr=to_dev(row_ptr), row_idx=to_dev(row_idx),
+    out = ops.finalize_posts(to_dev(np.array(bf.matrix)), row_ptr=to_dev(row_ptr), row_idx=to_dev(row_idx),
                              final_norm=True, want_f32=True, want_bf16=False)[0].cpu().numpy()
     want = []
     for frames in posts:                                   # the reference way, frame by frame
