@@ -191,28 +191,45 @@ __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__
       guess[q] = inv_w > 0.f ? lo : 0;
     }
     __syncthreads();
-    for (int64_t j = c0 + threadIdx.x; j < c1; j += blockDim.x) {
-      const float s = row[j];
-      if (ch == 0) before += ((s > bs) || (s == bs && (index_base + j) < bi)) ? 1ull : 0ull;
-      if (labels[j] == b) continue;          // negatives only (evaluator.py:112)
-      // number of positives e in this chunk with e > s  ==  m - upper_bound(spos, s)
-      int idx;
-      if (!(s >= lo_s)) idx = 0;             // below every positive (or NaN)
-      else if (s >= hi_s) idx = m;           // at or above every positive
-      else {
-        int q = (int)((s - lo_s) * inv_w);
-        q = q < 0 ? 0 : (q > kAucBuckets ? kAucBuckets : q);
-        idx = guess[q];
-        int steps = 0;
-        while (idx < m && spos[idx] <= s && steps < 8) { ++idx; ++steps; }
-        while (idx > 0 && spos[idx - 1] > s && steps < 8) { --idx; ++steps; }
-        if (steps >= 8) {                      // crowded bucket (ties / clustered positives): exact binary search
-          int lo = 0, hi = m;
-          while (lo < hi) { const int mid = (lo + hi) >> 1; if (spos[mid] > s) hi = mid; else lo = mid + 1; }
-          idx = lo;
-        }
+    // 8 independent (score, label) loads in flight per thread: the sweep is latency-bound otherwise
+    constexpr int U = 8;
+    unsigned int auc32 = 0, before32 = 0;      // per-batch partials stay 32-bit; folded into u64 per batch
+    for (int64_t j0 = c0 + threadIdx.x; j0 < c1; j0 += (int64_t)U * blockDim.x) {
+      float sv[U];
+      int lv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t j = j0 + (int64_t)u * blockDim.x;
+        sv[u] = j < c1 ? __ldg(row + j) : 0.f;
+        lv[u] = j < c1 ? __ldg(labels + j) : b;          // out of range: treated as a positive -> skipped
       }
-      auc += (unsigned long long)(m - idx);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t j = j0 + (int64_t)u * blockDim.x;
+        const float s = sv[u];
+        if (ch == 0 && j < c1) before32 += ((s > bs) || (s == bs && (index_base + j) < bi)) ? 1u : 0u;
+        if (lv[u] == b) continue;              // negatives only (evaluator.py:112)
+        // number of positives e in this chunk with e > s  ==  m - upper_bound(spos, s)
+        int idx;
+        if (!(s >= lo_s)) idx = 0;             // below every positive (or NaN)
+        else if (s >= hi_s) idx = m;           // at or above every positive
+        else {
+          int q = (int)((s - lo_s) * inv_w);
+          q = q < 0 ? 0 : (q > kAucBuckets ? kAucBuckets : q);
+          idx = guess[q];
+          int steps = 0;
+          while (idx < m && spos[idx] <= s && steps < 8) { ++idx; ++steps; }
+          while (idx > 0 && spos[idx - 1] > s && steps < 8) { --idx; ++steps; }
+          if (steps >= 8) {                      // crowded bucket (ties / clustered positives): exact binary search
+            int lo = 0, hi = m;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (spos[mid] > s) hi = mid; else lo = mid + 1; }
+            idx = lo;
+          }
+        }
+        auc32 += (unsigned int)(m - idx);
+      }
+      auc += auc32; before += before32;          // <= 8 * 8192 per batch: no 32-bit overflow
+      auc32 = 0; before32 = 0;
     }
   }
   // block reduce
