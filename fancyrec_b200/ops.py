@@ -68,6 +68,25 @@ def finalize_posts(visual, text=None, row_ptr=None, row_idx=None, visual_norm=Fa
     return out_f32, out_bf16
 
 
+def masked_mean_pool(x, lengths, l2norm=False):
+    """Mean over the first lengths[b] steps of every sequence: x [B, T, D] fp32, lengths [B] -> [B, D] fp32.
+    Replaces the per-sample Python loops `torch.mean(out[i][:len_i], 0)` of the reference encoders
+    (model.py:105-114, 163-168, 271-274, 344-346) with ONE pass of the pooling kernel: the padded steps are
+    skipped through the gather list, so only valid rows are read."""
+    _req(x, torch.float32, "x", 3)
+    b, t, d = x.shape
+    lengths = torch.as_tensor(lengths, device=x.device).to(torch.int64)
+    if lengths.numel() != b:
+        raise ValueError("lengths has %d entries, expected %d" % (lengths.numel(), b))
+    row_ptr = torch.zeros(b + 1, dtype=torch.int64, device=x.device)
+    row_ptr[1:] = torch.cumsum(lengths, 0)
+    steps = torch.arange(t, device=x.device)
+    valid = steps.unsqueeze(0) < lengths.unsqueeze(1)                                   # [B, T]
+    row_idx = (torch.arange(b, device=x.device).unsqueeze(1) * t + steps.unsqueeze(0))[valid].to(torch.int32)
+    return finalize_posts(x.reshape(b * t, d), row_ptr=row_ptr, row_idx=row_idx.contiguous(), final_norm=l2norm,
+                          want_f32=True, want_bf16=False)[0]
+
+
 def brand_embed(w, e, brand_ids=None, nb=None, tensor_cores=True):
     """A4: out[i] = mean_a W[ids[i], a] * E[a, :]  -> [nb, D] fp32.  tensor_cores: 3xTF32 tcgen05 GEMM (fp32-grade);
     False: fp32 FMA GEMM on the CUDA cores."""

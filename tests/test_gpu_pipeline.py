@@ -240,3 +240,19 @@ def test_bigfile_ingest_to_device(tmp_path):
         m = vecs.astype(np.float64).mean(0)
         want.append(m / np.sqrt((m * m).sum()))
     np.testing.assert_allclose(out, np.array(want), rtol=RTOL, atol=1e-7)
+
+
+def test_masked_mean_pool_matches_reference_loop():
+    """the encoders' per-sample `torch.mean(seq[:len], 0)` loops (model.py:105-114) as one
+    pass of the pooling kernel."""
+    from fancyrec_b200 import ops
+    rs = np.random.RandomState(23)
+    b, t, d = 17, 64, 256
+    x = rs.standard_normal((b, t, d)).astype(np.float32)
+    lengths = rs.randint(1, t + 1, b)
+    lengths[0], lengths[1] = t, 1
+    got = ops.masked_mean_pool(to_dev(x), lengths.tolist()).cpu().numpy()
+    want = np.stack([x[i, :lengths[i]].astype(np.float64).mean(0) for i in range(b)])
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-6)
+    gotn = ops.masked_mean_pool(to_dev(x), to_dev(lengths), l2norm=True).cpu().numpy()
+    np.testing.assert_allclose(gotn, want / np.linalg.norm(want, axis=1, keepdims=True), rtol=RTOL, atol=1e-6)
