@@ -320,10 +320,53 @@ __global__ void __launch_bounds__(256) finalize_block_kernel(FinalizeParams P) {
   for (int64_t p = blockIdx.x; p < P.n_posts; p += gridDim.x, buf ^= 1) {
     float4 x[VPT];
     float ssv = 0.f, sst = 0.f;
+    if (P.row_ptr == nullptr) {
 #pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-      const int c = (i * 256 + tid) * 4;
-      x[i] = c < d ? ld_row_f4(P, p, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < VPT; ++i) {
+        const int c = (i * 256 + tid) * 4;
+        x[i] = c < d ? ld_row_f4(P, p, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      // pooled visual branch: frames summed in order, 4 frames x (visual float4 of this thread) loads in flight
+      const int64_t r0 = P.row_ptr[p], r1 = P.row_ptr[p + 1];
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int64_t r = r0;
+      for (; r + 4 <= r1; r += 4) {
+        int64_t src[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) src[u] = P.row_idx ? (int64_t)P.row_idx[r + u] : r + u;
+        float4 f[4][VPT];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int i = 0; i < VPT; ++i) {
+            const int c = (i * 256 + tid) * 4;
+            f[u][i] = c < P.dv ? __ldg(reinterpret_cast<const float4*>(P.visual + src[u] * P.dv + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int i = 0; i < VPT; ++i) { x[i].x += f[u][i].x; x[i].y += f[u][i].y; x[i].z += f[u][i].z; x[i].w += f[u][i].w; }
+      }
+      for (; r < r1; ++r) {
+        const int64_t src = P.row_idx ? (int64_t)P.row_idx[r] : r;
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+          const int c = (i * 256 + tid) * 4;
+          if (c < P.dv) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(P.visual + src * P.dv + c));
+            x[i].x += f.x; x[i].y += f.y; x[i].z += f.z; x[i].w += f.w;
+          }
+        }
+      }
+      const float inv_f = 1.0f / (float)(r1 - r0);
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        const int c = (i * 256 + tid) * 4;
+        if (c < P.dv) { x[i].x *= inv_f; x[i].y *= inv_f; x[i].z *= inv_f; x[i].w *= inv_f; }
+        else if (c < d) x[i] = __ldg(reinterpret_cast<const float4*>(P.text + p * P.dt + (c - P.dv)));
+      }
     }
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
@@ -596,7 +639,7 @@ int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_
                    aligned16(out_bf16);
   int grid = (int)(n_posts < (int64_t)num_sms() * 8 ? n_posts : (int64_t)num_sms() * 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (vec && row_ptr == nullptr && d > 2048 && d <= 4096 && ld_bf16 % 4 == 0) {
+  if (vec && d > 2048 && d <= 4096 && ld_bf16 % 4 == 0) {       // long rows, pooled or not: block per row
     int64_t blocks = n_posts;
     const int64_t max_blocks = (int64_t)num_sms() * 8;
     if (blocks > max_blocks) blocks = max_blocks;
