@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(256) finalize_stream_kernel(FinalizeParams P) 
 // the row in registers (VPT float4 each, 12-16 registers), ONE block reduction per row (double-buffered
 // scratch -> a single __syncthreads), reciprocal scaling.  ~40 registers/thread -> 8 blocks = 64 warps per
 // SM keep the HBM pipe full while other blocks are in their reduction / store phase.
-template <int VPT>
+template <int VPT, bool POOLED>
 __global__ void __launch_bounds__(256) finalize_block_kernel(FinalizeParams P) {
   __shared__ float red[2][2][8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(256) finalize_block_kernel(FinalizeParams P) {
   for (int64_t p = blockIdx.x; p < P.n_posts; p += gridDim.x, buf ^= 1) {
     float4 x[VPT];
     float ssv = 0.f, sst = 0.f;
-    if (P.row_ptr == nullptr) {
+    if (!POOLED) {
 #pragma unroll
       for (int i = 0; i < VPT; ++i) {
         const int c = (i * 256 + tid) * 4;
@@ -643,9 +643,13 @@ int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_
     int64_t blocks = n_posts;
     const int64_t max_blocks = (int64_t)num_sms() * 8;
     if (blocks > max_blocks) blocks = max_blocks;
-    if (d <= 2048) finalize_block_kernel<2><<<(int)blocks, 256, 0, st>>>(P);
-    else if (d <= 3072) finalize_block_kernel<3><<<(int)blocks, 256, 0, st>>>(P);
-    else finalize_block_kernel<4><<<(int)blocks, 256, 0, st>>>(P);
+    if (row_ptr != nullptr) {
+      if (d <= 3072) finalize_block_kernel<3, true><<<(int)blocks, 256, 0, st>>>(P);
+      else finalize_block_kernel<4, true><<<(int)blocks, 256, 0, st>>>(P);
+    } else {
+      if (d <= 3072) finalize_block_kernel<3, false><<<(int)blocks, 256, 0, st>>>(P);
+      else finalize_block_kernel<4, false><<<(int)blocks, 256, 0, st>>>(P);
+    }
   } else if (vec && row_ptr == nullptr && d > 1024 && ld_bf16 % 4 == 0) {
     int64_t blocks = (n_posts + 7) / 8;
     const int64_t max_blocks = (int64_t)num_sms() * 8;
