@@ -317,14 +317,24 @@ __global__ void __launch_bounds__(256) finalize_block_kernel(FinalizeParams P) {
   const bool vn = (P.flags & FRX_VISUAL_NORM) != 0, tn = (P.flags & FRX_TEXT_NORM) != 0 && P.dt > 0;
   const bool fn = (P.flags & FRX_FINAL_NORM) != 0;
   int buf = 0;
+  float4 nxt[VPT];                                    // un-pooled path: next row's loads are issued one row ahead
+  if (!POOLED) {
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = (i * 256 + tid) * 4;
+      nxt[i] = (blockIdx.x < P.n_posts && c < d) ? ld_row_f4(P, blockIdx.x, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   for (int64_t p = blockIdx.x; p < P.n_posts; p += gridDim.x, buf ^= 1) {
     float4 x[VPT];
     float ssv = 0.f, sst = 0.f;
     if (!POOLED) {
+      const int64_t pn = p + gridDim.x;
 #pragma unroll
       for (int i = 0; i < VPT; ++i) {
         const int c = (i * 256 + tid) * 4;
-        x[i] = c < d ? ld_row_f4(P, p, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[i] = nxt[i];
+        nxt[i] = (pn < P.n_posts && c < d) ? ld_row_f4(P, pn, c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     } else {
       // pooled visual branch: frames summed in order, 4 frames x (visual float4 of this thread) loads in flight
