@@ -649,7 +649,7 @@ int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_
                    aligned16(out_bf16);
   int grid = (int)(n_posts < (int64_t)num_sms() * 8 ? n_posts : (int64_t)num_sms() * 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (vec && d > 2048 && d <= 4096 && ld_bf16 % 4 == 0) {       // long rows, pooled or not: block per row
+  if (vec && (d > 2048 || (d > 1024 && row_ptr == nullptr)) && d <= 4096 && ld_bf16 % 4 == 0) {   // long rows: block per row
     int64_t blocks = n_posts;
     const int64_t max_blocks = (int64_t)num_sms() * 8;
     if (blocks > max_blocks) blocks = max_blocks;
@@ -657,7 +657,8 @@ int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_
       if (d <= 3072) finalize_block_kernel<3, true><<<(int)blocks, 256, 0, st>>>(P);
       else finalize_block_kernel<4, true><<<(int)blocks, 256, 0, st>>>(P);
     } else {
-      if (d <= 3072) finalize_block_kernel<3, false><<<(int)blocks, 256, 0, st>>>(P);
+      if (d <= 2048) finalize_block_kernel<2, false><<<(int)blocks, 256, 0, st>>>(P);
+      else if (d <= 3072) finalize_block_kernel<3, false><<<(int)blocks, 256, 0, st>>>(P);
       else finalize_block_kernel<4, false><<<(int)blocks, 256, 0, st>>>(P);
     }
   } else if (vec && row_ptr == nullptr && d > 1024 && ld_bf16 % 4 == 0) {
