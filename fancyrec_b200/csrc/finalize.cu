@@ -609,6 +609,28 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
   }
 }
 
+// Same split for LONG operands (the post side of the score contraction, millions of rows): 128-bit loads and
+// stores, grid-stride over rows, one warp per row segment.  cols % 4 == 0, 16-byte aligned pointers.
+__global__ void __launch_bounds__(256) split_rows_vec_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ld_x,
+                                                             int pattern, float* __restrict__ out) {
+  const int c4 = cols >> 2;
+  const int64_t total = rows * (int64_t)c4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c4;
+    const int c = (int)(i - r * c4) << 2;
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(x + r * ld_x + c));
+    float4 hi, lo;
+    hi.x = tf32_round(v.x); lo.x = tf32_round(v.x - hi.x);
+    hi.y = tf32_round(v.y); lo.y = tf32_round(v.y - hi.y);
+    hi.z = tf32_round(v.z); lo.z = tf32_round(v.z - hi.z);
+    hi.w = tf32_round(v.w); lo.w = tf32_round(v.w - hi.w);
+    float* o = out + r * 3 * (int64_t)cols + c;
+    *reinterpret_cast<float4*>(o) = hi;
+    *reinterpret_cast<float4*>(o + cols) = pattern ? hi : lo;
+    *reinterpret_cast<float4*>(o + 2 * cols) = pattern ? lo : hi;
+  }
+}
+
 void launch_split_rows(const float* x, const int64_t* ids, int rows, int cols, int64_t ld_x, float scale, int pattern,
                        float* out, cudaStream_t st) {
   split_rows_kernel<<<rows, 256, 0, st>>>(x, ids, cols, ld_x, scale, pattern, out);
@@ -678,6 +700,27 @@ int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_
     if (smem > 48 * 1024) FRX_CUDA(cudaFuncSetAttribute(finalize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     finalize_kernel<1><<<grid, kFinThreads, smem, st>>>(P);
   }
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
+int frx_split_tf32x3(const float* x, int64_t rows, int cols, int64_t ld_x, int side, float* out, void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(x && out, "frx_split_tf32x3: NULL pointer");
+  FRX_CHECK_ARG(rows >= 0 && cols > 0 && ld_x >= cols, "frx_split_tf32x3: bad sizes rows=%lld cols=%d", (long long)rows, cols);
+  FRX_CHECK_ARG(side == 0 || side == 1, "frx_split_tf32x3: side must be 0 (brand) or 1 (post)");
+  FRX_CHECK_ARG(cols % 4 == 0 && ld_x % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0,
+                "frx_split_tf32x3: cols and ld_x must be multiples of 4 and the pointers 16-byte aligned");
+  int dev = 0;
+  FRX_CUDA(cudaGetDevice(&dev));
+  int rc = frx_device_check(dev);
+  if (rc) return rc;
+  if (rows == 0) return FRX_OK;
+  const int64_t total = rows * (int64_t)(cols / 4);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t max_blocks = (int64_t)num_sms() * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  split_rows_vec_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld_x, side, out);
   FRX_LAUNCH_CHECK();
   return FRX_OK;
 }

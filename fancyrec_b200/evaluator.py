@@ -39,10 +39,11 @@ def l2norm(X):
 
 def cal_sim(im, s):
     """Cosine similarity between every (brand, post) pair -> [M, N] fp32 on the device
-    (bf16 operands, fp32 accumulation; |error| <= 1e-3 on the cosine scale)."""
-    a = ranking.to_operand(im.contiguous().float())
-    b = ranking.to_operand(s.contiguous().float())
-    return ops.score_dense(a, b, d=im.shape[1])
+    (default: bf16 operands, fp32 accumulation, |error| <= 1e-3 on the cosine scale; ranking.PRECISION =
+    "tf32x3" gives |error| <= 1e-5 on the tf32 tensor-core path)."""
+    a = ranking.to_operand(im.contiguous().float(), side=ranking.BRAND_SIDE)
+    b = ranking.to_operand(s.contiguous().float(), side=ranking.POST_SIDE)
+    return ops.score_dense(a, b, d=ranking.contraction_depth(im.shape[1]))
 
 
 def random_sim(num_brands, num_test_posts):

@@ -87,6 +87,18 @@ def masked_mean_pool(x, lengths, l2norm=False):
                           want_f32=True, want_bf16=False)[0]
 
 
+def split_tf32x3(x, side):
+    """fp32 [N, D] -> the K-concatenated 3xTF32 operand [N, 3D] (side 0 = brand: [hi|lo|hi]; side 1 = post:
+    [hi|hi|lo]).  score_*(a3, b3, d=3D) on these gives fp32-grade scores on the tf32 tensor-core path."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x", 2)
+    out = torch.empty((x.shape[0], 3 * x.shape[1]), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.frx_split_tf32x3(_ptr(x), x.shape[0], x.shape[1], x.stride(0), int(side), _ptr(out), _stream(x))
+    _lib.check(rc, "frx_split_tf32x3")
+    return out
+
+
 def brand_embed(w, e, brand_ids=None, nb=None, tensor_cores=True):
     """A4: out[i] = mean_a W[ids[i], a] * E[a, :]  -> [nb, D] fp32.  tensor_cores: 3xTF32 tcgen05 GEMM (fp32-grade);
     False: fp32 FMA GEMM on the CUDA cores."""

@@ -14,16 +14,30 @@ MIN_TOPK = 64
 DENSE_BUDGET_BYTES = 2 << 30
 
 
-PRECISION = "bf16"      # "bf16" (default: 1e-3 score tolerance, full tensor rate) or "tf32" (2e-5, half rate)
+# Score precision (north_star: 1e-3 relative for bf16 inputs, 1e-5 for tf32):
+#   "bf16"    bf16 operands, fp32 accumulation, full tensor rate               |err| <= 1e-3   (default)
+#   "tf32"    fp32 operands read as tf32 (one pass, half rate)                 |err| <= 2e-4
+#   "tf32x3"  3xTF32 split operands (K = 3D, ~6x the bf16 time), fp32-grade    |err| <= 1e-5
+PRECISION = "bf16"
+BRAND_SIDE, POST_SIDE = 0, 1
 
 
-def to_operand(x_f32, final_norm=True, precision=None):
-    """fp32 [N, D] embeddings -> L2-normalised score operand: bf16 [N, round_up(D, 64)] (zero padded), or
-    fp32 [N, D] for the tf32 tensor-core path (D % 4 == 0)."""
-    if (precision or PRECISION) == "tf32":
+def contraction_depth(d, precision=None):
+    """K extent of the tensor-core contraction for embedding size d (3d for the K-concatenated 3xTF32 operands)."""
+    return 3 * d if (precision or PRECISION) == "tf32x3" else d
+
+
+def to_operand(x_f32, final_norm=True, precision=None, side=POST_SIDE):
+    """fp32 [N, D] embeddings -> L2-normalised score operand: bf16 [N, round_up(D, 64)] (zero padded), fp32
+    [N, D] for the tf32 path, or fp32 [N, 3D] (`side`-specific hi/lo layout) for the 3xTF32 path (D % 4 == 0)."""
+    precision = precision or PRECISION
+    if precision in ("tf32", "tf32x3"):
         if x_f32.shape[1] % 4:
             raise ValueError("tf32 operands need D % 4 == 0")
-        return ops.finalize_posts(x_f32, final_norm=final_norm, want_f32=True, want_bf16=False)[0]
+        unit = ops.finalize_posts(x_f32, final_norm=final_norm, want_f32=True, want_bf16=False)[0]
+        return ops.split_tf32x3(unit, side) if precision == "tf32x3" else unit
+    if precision != "bf16":
+        raise ValueError("unknown precision %r" % (precision,))
     return ops.finalize_posts(x_f32, final_norm=final_norm, want_f32=False, want_bf16=True)[1]
 
 
@@ -175,9 +189,9 @@ def side_stream(device):
 def rank_posts(brand_f32, post_f32, labels, k=MIN_TOPK, want_auc=True):
     """Single-GPU convenience: fp32 brand [NB, D] / post [NP, D] embeddings + labels -> (8-tuple, stats)."""
     labels_i32 = labels.to(torch.int32).contiguous()
-    d = post_f32.shape[1]
-    brand_bf16 = to_operand(brand_f32.contiguous().float())
-    post_bf16 = to_operand(post_f32.contiguous().float())
+    d = contraction_depth(post_f32.shape[1])
+    brand_bf16 = to_operand(brand_f32.contiguous().float(), side=BRAND_SIDE)
+    post_bf16 = to_operand(post_f32.contiguous().float(), side=POST_SIDE)
     dev_stats = device_rank_statistics(brand_bf16, post_bf16, labels_i32, d, k=k, want_auc=want_auc)
     stats = host_statistics(dev_stats, post_f32.shape[0], want_auc)
     return aggregate(stats, post_f32.shape[0], want_auc), stats, dev_stats

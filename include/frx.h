@@ -132,6 +132,15 @@ int frx_score_count(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* po
                     const float* thr_score, const int32_t* thr_index,
                     unsigned long long* count_out, void* stream);
 
+/* 3xTF32 operands (fp32-grade scores on the tensor cores, the mode that meets the 1e-5 score tolerance):
+ * x = hi + lo with hi, lo exactly representable in tf32; the K-concatenated operands
+ *   brand side (side 0): [hi | lo | hi]      post side (side 1): [hi | hi | lo]        (each [rows, 3 * cols] fp32)
+ * make ONE tf32 contraction over K = 3 * cols equal to a_hi.b_hi + a_lo.b_hi + a_hi.b_lo = a.b up to O(2^-22).
+ * Feed the results to the frx_score_*_tf32 entry points with d = 3 * cols: same kernels, same fused top-k,
+ * ~6x the bf16 time.  Replaces nothing in the reference -- it is how cal_sim's fp32 mm (evaluator.py:29) is
+ * matched to 1e-5 without leaving the tensor cores.  cols % 4 == 0, ld_x % 4 == 0, 16-byte aligned pointers. */
+int frx_split_tf32x3(const float* x, int64_t rows, int cols, int64_t ld_x, int side, float* out, void* stream);
+
 /* tf32 variants: identical contracts, operands are fp32 [rows, ld] (rows L2-normalised, ld % 4 == 0, 16-byte aligned base),
  * read by the tensor cores as tf32 (10-bit mantissa, tcgen05.mma.kind::tf32) with fp32 accumulation: scores within 2e-4 of
  * fp32 cal_sim at D >= 1024 on the cosine scale (observed 1.1e-4), at half the bf16 tensor throughput and twice the operand bytes. */

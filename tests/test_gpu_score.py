@@ -97,8 +97,8 @@ def test_tf32_path(nb, npost, d, k):
     ref = oref.cal_sim(brand, posts)
     # tf32 keeps 10 mantissa bits (operands truncated by the tensor core): <= 2 * 2^-10 worst case on the
     # cosine scale; stated tolerance 2e-4 at D >= 1024 (observed 1.1e-4 at D = 1024: per-product relative
-    # error ~4e-4 averaged over D terms).  north_star's 1e-5 is not reachable by a single tf32 pass; it would
-    # need a 3xTF32 split at 3x the cost.
+    # error ~4e-4 averaged over D terms).  north_star's 1e-5 is not reachable by a single tf32 pass: that is
+    # what precision "tf32x3" is for (next test).
     err = float(np.abs(dense - ref).max())
     print("tf32 max |score - fp32 cal_sim| at D=%d: %.3e" % (d, err))
     assert err <= (2e-4 if d >= 1024 else 2.0 ** -9)
@@ -112,6 +112,49 @@ def test_tf32_path(nb, npost, d, k):
                           index_base=5).cpu().numpy()
     for r in range(0, nb, max(1, nb // 8)):
         assert cnt[r] == int(np.where(oref.order_desc(dense[r]) == tj[r])[0][0])
+
+
+@pytest.mark.parametrize("nb,npost,d,k", [(130, 3000, 1024, 100), (64, 2000, 3072, 64), (40, 300000, 64, 64),
+                                          (7, 513, 52, 10)])
+def test_tf32x3_path_meets_1e5(nb, npost, d, k):
+    """3xTF32 split operands (K = 3D) through the same tf32 kernels: scores within north_star's 1e-5 of
+    fp32 cal_sim (relative, on the cosine scale |s| <= 1: |ours - ref| <= 1e-5), rankings exact on our scores."""
+    from fancyrec_b200 import ops, ranking
+    rs = np.random.RandomState(nb + d + 1)
+    brand = rs.standard_normal((nb, d)).astype(np.float32)
+    posts = rs.standard_normal((npost, d)).astype(np.float32)
+    lab = synth.labels(3, npost, nb)
+    a = ranking.to_operand(to_dev(brand), precision="tf32x3", side=ranking.BRAND_SIDE)
+    b = ranking.to_operand(to_dev(posts), precision="tf32x3", side=ranking.POST_SIDE)
+    assert a.shape == (nb, 3 * d) and b.shape == (npost, 3 * d) and a.dtype == torch.float32
+    kd = ranking.contraction_depth(d, "tf32x3")
+    dense = ops.score_dense(a, b, d=kd).cpu().numpy()
+    ref = oref.cal_sim(brand, posts)                       # fp64-accumulated cosine, the oracle of evaluator.py:23-29
+    err = float(np.abs(dense - ref).max())
+    print("tf32x3 max |score - cal_sim| at D=%d: %.3e" % (d, err))
+    assert err <= 1e-5
+    res = ops.score_topk(a, b, k, d=kd, labels=to_dev(lab.astype(np.int32)), index_base=5)
+    want = oref.topk_indices(dense, k)
+    assert np.array_equal(res["index"].cpu().numpy(), want + 5)
+    assert np.array_equal(res["scores"].cpu().numpy(), np.take_along_axis(dense, want, 1))
+    assert np.array_equal(res["pos_score"].cpu().numpy(), dense[lab, np.arange(npost)])
+
+
+def test_tf32x3_through_public_api(monkeypatch):
+    """ranking.PRECISION = 'tf32x3' switches cal_sim / rank_posts to the fp32-grade path."""
+    from fancyrec_b200 import evaluator, ranking
+    monkeypatch.setattr(ranking, "PRECISION", "tf32x3")
+    rs = np.random.RandomState(5)
+    nb, npost, d = 50, 4000, 1024
+    brand = rs.standard_normal((nb, d)).astype(np.float32)
+    posts = rs.standard_normal((npost, d)).astype(np.float32)
+    lab = synth.labels(9, npost, nb)
+    ours = evaluator.cal_sim(to_dev(brand), to_dev(posts)).cpu().numpy()
+    assert np.abs(ours - oref.cal_sim(brand, posts)).max() <= 1e-5
+    result, stats, _ = ranking.rank_posts(to_dev(brand), to_dev(posts), to_dev(lab), want_auc=True)
+    want = oref.rank_metrics_vec(ours, lab)
+    assert tuple(map(float, result)) == tuple(map(float, want))
+    assert np.array_equal(stats["auc_num"], oref.rank_stats(ours, lab)["auc_num"])
 
 
 def test_heavy_ties_and_index_base():
