@@ -41,6 +41,10 @@ constexpr int NUM_THREADS = (EPI_WARP0 + NUM_EPI_WARPS) * 32;   // 384
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_MERGE_KEYS = 16384;
 constexpr int64_t kSampleMinPosts = 262144;   // below this the warm-up is too short to be worth a sample pass
+// Global per-row candidate histogram (TOPK): bin = (ordered(score) - ordered(sample threshold)) >> HIST_SHIFT, i.e.
+// 64 bins over one octave of the score above the seeded threshold; the last bin also holds everything beyond.
+constexpr int HIST_BINS = 64, HIST_SHIFT = 17;
+constexpr int REFINE_EVERY = 4;               // tiles between two threshold refinements of a (row, column half)
 
 enum Mode { MODE_TOPK = 0, MODE_DENSE = 1, MODE_COUNT = 2 };
 
@@ -57,6 +61,8 @@ struct ScoreParams {
   unsigned long long* part_keys;   // [items][2 column halves][128][cap]
   int* part_cnt;                   // [items][2][128]
   uint32_t* row_thr;               // [nb] best published lower bound of each row's k-th best score (ordered)
+  uint32_t* row_hist;              // [nb][HIST_BINS] scores appended so far by ANY CTA, binned above row_base (nullptr = off)
+  const uint32_t* row_base;        // [nb] ordered threshold seeded by the sample pass = origin of the bins (0 = row off)
   const int32_t* labels;
   float* pos_score;
   // DENSE
@@ -200,6 +206,29 @@ __device__ __forceinline__ int select_dispatch(int cap, unsigned long long* buf,
   return warp_select<0>(buf, n, k, keep_limit, exact, hist, thr_out);
 }
 
+// Threshold refinement from the row's global histogram: the highest bin whose suffix count reaches k.  At least k
+// posts seen so far (by any CTA) score at or above that bin's lower edge, so the edge is a valid lower bound of the
+// row's global k-th best score -- every CTA of the row may drop everything below it.  -1 = fewer than k counted.
+__device__ __forceinline__ int hist_edge(const uint32_t* hrow, uint32_t k) {
+  uint32_t acc = 0;
+  int reached = 0;                               // number of bins b with suffix(b) >= k (suffix is non-increasing in b)
+#pragma unroll
+  for (int half = 1; half >= 0; --half) {
+    uint4 c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = __ldcg(reinterpret_cast<const uint4*>(hrow) + half * 8 + i);
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      acc += c[i].w; reached += acc >= k;
+      acc += c[i].z; reached += acc >= k;
+      acc += c[i].y; reached += acc >= k;
+      acc += c[i].x; reached += acc >= k;
+    }
+    if (reached) return half * 32 + reached - 1;
+  }
+  return -1;
+}
+
 template <int MODE, bool TF32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -314,6 +343,12 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       unsigned long long* rowbuf = nullptr;
       float ts = 0.f; int32_t ti = -1; unsigned long long ccount = 0;
       if (MODE == MODE_TOPK) rowbuf = P.part_keys + (part + row_in_tile) * P.cap;
+      uint32_t hbase = 0;                            // TOPK: origin of this row's histogram bins (0 = off)
+      uint32_t* hrow = nullptr;
+      if (MODE == MODE_TOPK && P.row_hist != nullptr && row_ok) {
+        hbase = __ldg(P.row_base + row);
+        hrow = P.row_hist + (size_t)row * HIST_BINS;
+      }
       if (MODE == MODE_COUNT && row_ok) { ts = P.thr_score[row]; ti = P.thr_index[row]; }
 
       for (int64_t t = t0; t < t1; ++t) {
@@ -330,6 +365,19 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             }
           }
           if (row_ok) thr = fmaxf(thr, ordered_to_score(__ldcg(P.row_thr + row)));
+          // every REFINE_EVERY tiles (the two column halves alternate): re-derive the threshold from what ALL CTAs
+          // of this row have appended so far and publish it
+          if (P.row_hist != nullptr && ((int)(t - t0) % REFINE_EVERY) == (h ? REFINE_EVERY / 2 : 0) && hbase != 0u) {
+            const int edge = hist_edge(hrow, (uint32_t)P.k);
+            if (edge > 0) {
+              const uint32_t eo = hbase + ((uint32_t)edge << HIST_SHIFT);
+              const float nt = ordered_to_score(eo);
+              if (nt == nt && nt > thr) {
+                thr = nt;
+                atomicMax(P.row_thr + row, eo);
+              }
+            }
+          }
         }
         mbar_wait(smem_u32(&tail->tmem_full[as]), aphase);
         tc_fence_after();
@@ -388,8 +436,13 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                   for (int j = 0; j < 4; ++j) {
                     const int i = 4 * g4 + j;
                     if ((hm >> i) & 1u) {
-                      rowbuf[cnt] = make_key(__uint_as_float(v[i]), gbase + i);
+                      const uint32_t so = score_to_ordered(__uint_as_float(v[i]));
+                      rowbuf[cnt] = ((unsigned long long)so << 32) | (unsigned long long)(0xFFFFFFFFu - (gbase + i));
                       ++cnt;
+                      if (hbase != 0u) {
+                        const uint32_t bin = (so - hbase) >> HIST_SHIFT;     // so >= ordered(thr) >= hbase
+                        atomicAdd(hrow + (bin < (uint32_t)(HIST_BINS - 1) ? bin : (uint32_t)(HIST_BINS - 1)), 1u);
+                      }
                     }
                   }
                 }
@@ -522,7 +575,6 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long
   __shared__ int kept;
   __shared__ uint32_t hist[256];
   __shared__ int sel[3];
-  (void)row_thr;
   const int b = blockIdx.x, m_tile = b / BM, r = b % BM;
   const int lists = splits * 2;                 // (split, column half) -> list (split*num_m_tiles + m_tile)*2 + half
   auto list_ptr = [&](int s) {
@@ -540,7 +592,7 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long
   }
   __syncthreads();
   int total = offs[lists];
-  const bool staged = total + (total > k ? k : 0) <= smem_keys;
+  bool staged = total + (total > k ? k : 0) <= smem_keys;
   // flattened element g -> key (global path)
   auto fetch = [&](int g) -> unsigned long long {
     int lo = 0, hi = lists;                      // largest s with offs[s] <= g
@@ -554,6 +606,30 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long
       for (int i = threadIdx.x; i < n; i += blockDim.x) skeys[offs[s] + i] = src[i];
     }
     __syncthreads();
+  } else {
+    // Too many candidates for shared memory: most of them were appended under an early, loose threshold.  Keep only
+    // those that reach the row's FINAL published threshold (a lower bound of the k-th best, so no top-k entry is
+    // lost); when the survivors fit, carry on in shared memory, else stream everything from global memory.
+    const unsigned long long min_key = (unsigned long long)row_thr[b] << 32;
+    const int room = smem_keys - k;
+    for (int g0 = threadIdx.x; g0 < total; g0 += 8 * 256) {
+      unsigned long long kk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const int g = g0 + j * 256; kk[j] = g < total ? fetch(g) : 0ull; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (g0 + j * 256 < total && kk[j] >= min_key) {
+          const int slot = atomicAdd(&kept, 1);
+          if (slot < room) skeys[slot] = kk[j];
+        }
+      }
+    }
+    __syncthreads();
+    const int nf = kept;
+    __syncthreads();
+    if (threadIdx.x == 0) kept = 0;
+    __syncthreads();
+    if (nf <= room) { total = nf; staged = true; }
   }
   if (total > k) {
     // block-wide MSB-first radix select of the k-th best key (exact; keys are unique)
@@ -808,8 +884,9 @@ struct TopkLayout {
   Plan main, sample;
   bool has_sample, sample_dense;
   int64_t n_s, stride;
-  size_t cnt_bytes, thr_bytes, keys_bytes, dense_bytes;
-  size_t total() const { return cnt_bytes + thr_bytes + keys_bytes + dense_bytes + 256; }
+  size_t cnt_bytes, thr_bytes, keys_bytes, dense_bytes, hist_bytes;
+  // [part_cnt | row_thr | row_base | row_hist | part_keys | sample dense tile]
+  size_t total() const { return cnt_bytes + 2 * thr_bytes + hist_bytes + keys_bytes + dense_bytes + 256; }
 };
 
 static TopkLayout make_topk_layout(int nb, int64_t n_posts, int k) {
@@ -818,6 +895,7 @@ static TopkLayout make_topk_layout(int nb, int64_t n_posts, int k) {
   L.cnt_bytes = L.main.cnt_bytes;
   L.keys_bytes = L.main.keys_bytes;
   L.thr_bytes = L.main.thr_bytes;
+  L.hist_bytes = (size_t)nb * HIST_BINS * sizeof(uint32_t);
   L.has_sample = n_posts >= kSampleMinPosts;
   if (L.has_sample) {
     int64_t n_s = n_posts / 64;
@@ -997,7 +1075,10 @@ static int score_topk_impl(const void* a, int64_t ld_a, const void* b, int64_t l
   P.keep_limit = plan.keep_limit;
   P.part_cnt = reinterpret_cast<int*>(workspace);
   P.row_thr = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + L.cnt_bytes);
-  P.part_keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(workspace) + L.cnt_bytes + L.thr_bytes);
+  uint8_t* const ws8 = reinterpret_cast<uint8_t*>(workspace);
+  uint32_t* const row_base = reinterpret_cast<uint32_t*>(ws8 + L.cnt_bytes + L.thr_bytes);
+  uint32_t* const row_hist = reinterpret_cast<uint32_t*>(ws8 + L.cnt_bytes + 2 * L.thr_bytes);
+  P.part_keys = reinterpret_cast<unsigned long long*>(ws8 + L.cnt_bytes + 2 * L.thr_bytes + L.hist_bytes);
   FRX_CUDA(cudaMemsetAsync(P.row_thr, 0, L.thr_bytes, st));        // ordered 0 = below every score
   P.labels = labels;
   P.pos_score = pos_score;
@@ -1009,7 +1090,8 @@ static int score_topk_impl(const void* a, int64_t ld_a, const void* b, int64_t l
     size_t np2 = 2;
     while (np2 < (size_t)2 * k) np2 <<= 1;
     size_t mkeys = total_max + k;
-    if (mkeys > (size_t)MAX_MERGE_KEYS + 1024) mkeys = np2;
+    if (mkeys > (size_t)MAX_MERGE_KEYS + 1024) mkeys = (size_t)8 * k + 1024;   // room for the threshold-filtered candidates
+    if (mkeys > (size_t)MAX_MERGE_KEYS + 1024) mkeys = (size_t)MAX_MERGE_KEYS + 1024;
     if (mkeys < np2) mkeys = np2;
     const size_t msmem = mkeys * sizeof(unsigned long long);
     if (msmem > 32 * 1024)   // static smem (~10 KB) counts against the 48 KB default too
@@ -1025,7 +1107,7 @@ static int score_topk_impl(const void* a, int64_t ld_a, const void* b, int64_t l
   // best, so the main pass starts with a pass rate of ~k/n_sample instead of warming every candidate
   // list up from -inf; candidates appended per row drop by an order of magnitude.
   if (L.has_sample && L.sample_dense) {
-    float* sdense = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + L.cnt_bytes + L.thr_bytes + L.keys_bytes);
+    float* sdense = reinterpret_cast<float*>(ws8 + L.cnt_bytes + 2 * L.thr_bytes + L.hist_bytes + L.keys_bytes);
     ScoreParams S{};
     S.dense = sdense;
     S.ld_dense = L.n_s;
@@ -1052,6 +1134,15 @@ static int score_topk_impl(const void* a, int64_t ld_a, const void* b, int64_t l
     if (rc) return rc;
     seed_threshold_kernel<<<(nb + 255) / 256, 256, 0, st>>>(topk_scores, nb, k, P.row_thr);
     FRX_LAUNCH_CHECK();
+  }
+  // The seeded thresholds are the origin of the per-row candidate histograms through which the CTAs of a row share
+  // how many scores above each level have been seen so far (see hist_edge): the append threshold then tracks the
+  // k-th best of everything processed by ANY CTA, not only of the CTA's own slice.
+  if (L.has_sample) {
+    FRX_CUDA(cudaMemcpyAsync(row_base, P.row_thr, L.thr_bytes, cudaMemcpyDeviceToDevice, st));
+    FRX_CUDA(cudaMemsetAsync(row_hist, 0, L.hist_bytes, st));
+    P.row_base = row_base;
+    P.row_hist = row_hist;
   }
   rc = launch_score<MODE_TOPK, TF32>(a, ld_a, b, ld_b, nb, n_posts, d, plan, P, st);
   if (rc) return rc;
