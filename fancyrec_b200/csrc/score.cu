@@ -22,6 +22,7 @@
 // A work item is (m_tile, split): 128 brand rows x a contiguous range of 256-post tiles.  Items are
 // numbered split-major so that the CTAs resident at any time read the same post range (served by L2).
 // Per-item candidate lists are merged by merge_partials_kernel (bitonic sort of <= 16384 keys in smem).
+#include <stdlib.h>
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -42,9 +43,10 @@ constexpr int TMEM_COLS = 512;
 constexpr int MAX_MERGE_KEYS = 16384;
 constexpr int64_t kSampleMinPosts = 262144;   // below this the warm-up is too short to be worth a sample pass
 // Global per-row candidate histogram (TOPK): bin = (ordered(score) - ordered(sample threshold)) >> HIST_SHIFT, i.e.
-// 64 bins over one octave of the score above the seeded threshold; the last bin also holds everything beyond.
-constexpr int HIST_BINS = 64, HIST_SHIFT = 17;
-constexpr int REFINE_EVERY = 4;               // tiles between two threshold refinements of a (row, column half)
+// 64 bins over two octaves of the score above the seeded threshold (32 per octave: the refined threshold sits at most
+// ~3 % below the true k-th best); the last bin also holds everything beyond.
+constexpr int HIST_BINS = 64, HIST_SHIFT = 18;
+constexpr int REFINE_EVERY = 8;               // tiles between two threshold refinements of a (row, column half)
 
 enum Mode { MODE_TOPK = 0, MODE_DENSE = 1, MODE_COUNT = 2 };
 
@@ -63,6 +65,7 @@ struct ScoreParams {
   uint32_t* row_thr;               // [nb] best published lower bound of each row's k-th best score (ordered)
   uint32_t* row_hist;              // [nb][HIST_BINS] scores appended so far by ANY CTA, binned above row_base (nullptr = off)
   const uint32_t* row_base;        // [nb] ordered threshold seeded by the sample pass = origin of the bins (0 = row off)
+  int refine_every;                // tiles between two threshold refinements of a (row, column half)
   const int32_t* labels;
   float* pos_score;
   // DENSE
@@ -367,7 +370,7 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           if (row_ok) thr = fmaxf(thr, ordered_to_score(__ldcg(P.row_thr + row)));
           // every REFINE_EVERY tiles (the two column halves alternate): re-derive the threshold from what ALL CTAs
           // of this row have appended so far and publish it
-          if (P.row_hist != nullptr && ((int)(t - t0) % REFINE_EVERY) == (h ? REFINE_EVERY / 2 : 0) && hbase != 0u) {
+          if (P.row_hist != nullptr && ((int)(t - t0) % P.refine_every) == (h ? P.refine_every / 2 : 0) && hbase != 0u) {
             const int edge = hist_edge(hrow, (uint32_t)P.k);
             if (edge > 0) {
               const uint32_t eo = hbase + ((uint32_t)edge << HIST_SHIFT);
@@ -734,8 +737,12 @@ __global__ void __launch_bounds__(256) row_kth_kernel(const float* __restrict__ 
       const bool on = i < n && (pass == 0 || (key >> (shift + 8)) == prefix);
       // scores cluster in a few digits (same sign/exponent): one shared-memory atomic per distinct digit per warp
       const uint32_t digit = on ? ((key >> shift) & 255u) : 0xFFFFFFFFu;
-      const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-      if (on && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+      if (pass == 0) {
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        if (on && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+      } else if (on) {
+        atomicAdd(&hist[digit], 1u);              // later digits are mantissa bits: spread out, few lanes active
+      }
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -898,17 +905,17 @@ static TopkLayout make_topk_layout(int nb, int64_t n_posts, int k) {
   L.hist_bytes = (size_t)nb * HIST_BINS * sizeof(uint32_t);
   L.has_sample = n_posts >= kSampleMinPosts;
   if (L.has_sample) {
-    int64_t n_s = n_posts / 64;
-    n_s = n_s < 8192 ? 8192 : (n_s > 32768 ? 32768 : n_s);
-    if (n_s < 32 * (int64_t)k) n_s = 32 * (int64_t)k;          // keep the seeded pass rate k / n_s at <= 3 %
-    if (n_s > 32768) n_s = 32768;
-    if (n_s > n_posts / 16) n_s = n_posts / 16;                // never spend more than ~6 % extra on the sample
+    // The sample only has to put the seeded threshold within the histogram's range (two octaves) of the final
+    // k-th best score; the refinement does the rest.  16 k posts ... 4096 at least, 32768 at most, <= 1/16 of the posts.
+    int64_t n_s = 16 * (int64_t)k;
+    n_s = n_s < 4096 ? 4096 : (n_s > 32768 ? 32768 : n_s);
+    if (n_s > n_posts / 16) n_s = n_posts / 16;
     if (n_s < 4 * (int64_t)k) n_s = 4 * (int64_t)k;
     n_s = (n_s + BN - 1) / BN * BN;
     L.n_s = n_s;
     L.stride = n_posts / n_s;
     // small enough: dense sample tile + per-row k-th select (cheapest); else the fused top-k kernel on the sample
-    L.sample_dense = (size_t)nb * (size_t)n_s * sizeof(float) <= ((size_t)256 << 20) && n_s <= 32768;
+    L.sample_dense = (size_t)nb * (size_t)n_s * sizeof(float) <= ((size_t)1 << 30) && n_s <= 32768;
     if (L.sample_dense) {
       L.sample = make_plan(nb, n_s, 1, MODE_DENSE);
       L.dense_bytes = (((size_t)nb * (size_t)n_s * sizeof(float)) + 255) & ~(size_t)255;
@@ -1143,6 +1150,8 @@ static int score_topk_impl(const void* a, int64_t ld_a, const void* b, int64_t l
     FRX_CUDA(cudaMemsetAsync(row_hist, 0, L.hist_bytes, st));
     P.row_base = row_base;
     P.row_hist = row_hist;
+    static const int refine_env = getenv("FRX_REFINE_EVERY") ? atoi(getenv("FRX_REFINE_EVERY")) : 0;   // tuning knob
+    P.refine_every = refine_env >= 2 ? refine_env : REFINE_EVERY;
   }
   rc = launch_score<MODE_TOPK, TF32>(a, ld_a, b, ld_b, nb, n_posts, d, plan, P, st);
   if (rc) return rc;

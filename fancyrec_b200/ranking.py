@@ -129,17 +129,16 @@ def _ideal_table(depth):
     return tab
 
 
-def _ndcg_rows(hits, n_pos, k, n_posts):
-    """ndcg_at_k (util/ndcg.py:48-78) for every row of a 0/1 `hits` matrix at once.  Row reductions run
+def _ndcg_rows(hits_f64, n_pos, k, n_posts):
+    """ndcg_at_k (util/ndcg.py:48-78) for every row of a 0/1 `hits` matrix (float64) at once.  Row reductions run
     over the contiguous last axis, so NumPy applies to each row the same pairwise summation it applies
     to the reference's 1-D np.sum -- results are bit-identical (tests/test_abi.py checks this)."""
-    depth = min(k, n_posts, hits.shape[1])
+    depth = min(k, n_posts, hits_f64.shape[1])
     table, disc = _ideal_table(depth)
-    r = np.ascontiguousarray(hits[:, :depth], dtype=np.float64)
     if depth > 1:
-        dcg = r[:, 0] + np.sum(np.ascontiguousarray(r[:, 1:] / disc), axis=1)
+        dcg = hits_f64[:, 0] + np.sum(np.ascontiguousarray(hits_f64[:, 1:depth] / disc), axis=1)
     else:
-        dcg = r[:, 0].copy()
+        dcg = hits_f64[:, 0].copy()
     best = table[np.minimum(n_pos, depth)]
     out = np.zeros(len(n_pos), dtype=np.float64)
     nz = best != 0
@@ -167,7 +166,7 @@ def aggregate(stats, n_posts, want_auc=True):
         auc = np.average(num / den)
     else:
         auc = np.float64("nan")
-    hits = np.asarray(stats["hits"])[has]
+    hits = np.asarray(stats["hits"])[has].astype(np.float64)
     n10 = _ndcg_rows(hits, n_pos[has], 10, n_posts)
     n50 = _ndcg_rows(hits, n_pos[has], 50, n_posts)
     return (np.floor(np.median(first)), np.floor(np.mean(first)), auc,
