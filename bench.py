@@ -197,6 +197,24 @@ def _claim_stdout():
     return lambda text: os.write(saved, (text + "\n").encode())
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this process to the CPU cores NVML reports as local to its GPU, so that the pinned host buffers of the
+    e2e leg are allocated on the GPU's own NUMA node (8 ranks sharing one socket's memory halve the H2D rate)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local_rank)
+        try:
+            bus = "%08X:%02X:%02X.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def run_ours(args):
     emit = _claim_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -205,6 +223,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cores = bind_to_gpu_numa(local_rank) if world > 1 else None
     if world > 1:
         os.environ["NCCL_DEBUG"] = os.environ.get("FRX_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         torch.distributed.init_process_group("nccl", device_id=dev)
@@ -278,7 +297,7 @@ def run_ours(args):
                        "brands": nb, "posts_per_gpu": n_local, "posts_total": n_local * world, "dim": d, "k": cfg["k"],
                        "sharding": "posts x %d, one all-gather of top-k lists" % world,
                        "cache": "inputs larger than L2 (12.3 GB fp32 + 6.1 GB bf16 per step vs 126 MB)",
-                       "seed": SEED0},
+                       "seed": SEED0, "host_cores_bound_to_gpu_numa_node": numa_cores},
             "clocks": clocks,
             "gpu_launches": ev.launches * args.steps,
             "roofline": {"bound": "tensor", "kernel": "frx::score_kernel<MODE_TOPK> (tcgen05 bf16, fused top-k)",

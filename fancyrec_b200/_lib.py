@@ -40,6 +40,10 @@ SIGNATURES = {
     "frx_contrastive_workspace_bytes": (c_sz, [c_i32, c_i32, c_i32]),
     "frx_contrastive_fwd_bwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_f32, c_f32, c_i32,
                                         c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "frx_crossclr_workspace_bytes": (c_sz, [c_i32, c_i32]),
+    "frx_crossclr_fwd_bwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "frx_lab_workspace_bytes": (c_sz, [c_i32, c_i32]),
+    "frx_lab_fwd_bwd": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "frx_normalize_rows": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp]),
     "frx_probe_enable": (c_i32, [c_i32]),
     "frx_probe_read": (c_i32, [c_vp, c_i32]),

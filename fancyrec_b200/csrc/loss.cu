@@ -287,6 +287,145 @@ __global__ void add3_kernel(const float* __restrict__ a, const float* __restrict
     out[i] = a[i] + b[i] + (c ? c[i] : 0.f);
 }
 
+// ---------------------------------------------------------------------------------------------
+// A14: CrossCLR_onlyIntraModality (loss_ctrs.py:52-117) and LabLoss (loss.py:55-63) on the same tile machinery.
+// ---------------------------------------------------------------------------------------------
+// Row i of both soft-maxes of CrossCLR.  Logits (already / T):  lbp[i,j] = bn_i.pn_j,  lbb = bn.bn^T,  lpp = pn.pn^T.
+//   brand side: [ lbp[i,:] , w * lbb[i,:] with the diagonal entry replaced by 0 ]      weight rank_b[i]
+//   post side:  [ lbp[:,i] , w * lpp[i,:] with the diagonal entry replaced by 0 ]      weight rank_p[i]
+// (the reference multiplies the intra logits by an off-diagonal mask, loss_ctrs.py:97-99, so the diagonal stays
+// in the soft-max as a logit of 0).  Writes d loss / d logits:
+//   g1[i,:]  brand side w.r.t. lbp[i,:]        g2[i,:]  post side w.r.t. lbp[:,i]  (i.e. the TRANSPOSED position)
+//   lbb[i,:] and lpp[i,:] are overwritten by their own gradients.
+__global__ void __launch_bounds__(256) crossclr_row_kernel(const float* __restrict__ lbp, float* __restrict__ lbb,
+                                                            float* __restrict__ lpp, int b, float neg_w, float scale,
+                                                            const float* __restrict__ rank_p, const float* __restrict__ rank_b,
+                                                            float* __restrict__ g1, float* __restrict__ g2,
+                                                            float* __restrict__ partial) {
+  __shared__ float red[8];
+  const int i = blockIdx.x;
+  const float* brow = lbp + (int64_t)i * b;
+  float* bb = lbb + (int64_t)i * b;
+  float* pp = lpp + (int64_t)i * b;
+  // soft-max maxima (F.softmax subtracts the row maximum)
+  float mb = 0.f, mp = 0.f;                       // the zeroed diagonal intra logit is always present
+  for (int j = threadIdx.x; j < b; j += blockDim.x) {
+    mb = fmaxf(mb, brow[j]);
+    mp = fmaxf(mp, lbp[(int64_t)j * b + i]);
+    if (j != i) { mb = fmaxf(mb, neg_w * bb[j]); mp = fmaxf(mp, neg_w * pp[j]); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+    mp = fmaxf(mp, __shfl_xor_sync(0xffffffffu, mp, o));
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mb;
+  __syncthreads();
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mb = fmaxf(mb, red[w]);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mp;
+  __syncthreads();
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mp = fmaxf(mp, red[w]);
+  float zb = 0.f, zp = 0.f;
+  for (int j = threadIdx.x; j < b; j += blockDim.x) {
+    zb += expf(brow[j] - mb) + expf((j == i ? 0.f : neg_w * bb[j]) - mb);
+    zp += expf(lbp[(int64_t)j * b + i] - mp) + expf((j == i ? 0.f : neg_w * pp[j]) - mp);
+  }
+  zb = block_sum_float(zb, red);
+  zp = block_sum_float(zp, red);
+  const float wb = rank_b[i], wp = rank_p[i];
+  const float dii = brow[i];
+  __syncthreads();
+  for (int j = threadIdx.x; j < b; j += blockDim.x) {
+    const float sb = expf(brow[j] - mb) / zb, sp = expf(lbp[(int64_t)j * b + i] - mp) / zp;
+    g1[(int64_t)i * b + j] = scale * wb * (sb - (j == i ? 1.f : 0.f));
+    g2[(int64_t)i * b + j] = scale * wp * (sp - (j == i ? 1.f : 0.f));
+    const float nb_ = bb[j], np_ = pp[j];
+    bb[j] = j == i ? 0.f : scale * wb * neg_w * expf(neg_w * nb_ - mb) / zb;
+    pp[j] = j == i ? 0.f : scale * wp * neg_w * expf(neg_w * np_ - mp) / zp;
+  }
+  if (threadIdx.x == 0) partial[i] = wb * (mb + logf(zb) - dii) + wp * (mp + logf(zp) - dii);
+}
+
+// xb[i, :] = [ g1[i,j] + g2[j,i] | gbb[i,j] + gbb[j,i] ]     (d loss / d (bn.pn^T) and the symmetrised intra gradient)
+// xp[i, :] = [ g1[j,i] + g2[i,j] | gpp[i,j] + gpp[j,i] ]     both [b, 2b] row-major
+__global__ void __launch_bounds__(256) crossclr_combine_kernel(const float* __restrict__ g1, const float* __restrict__ g2,
+                                                                const float* __restrict__ gbb, const float* __restrict__ gpp,
+                                                                int b, float* __restrict__ xb, float* __restrict__ xp) {
+  __shared__ float t1[32][33], t2[32][33], tb[32][33], tp[32][33];
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < 32; r += 8) {                 // transposed block (rows j0.., cols i0..)
+    const int jj = j0 + ty + r, ii = i0 + tx;
+    const bool ok = jj < b && ii < b;
+    t1[ty + r][tx] = ok ? g1[(int64_t)jj * b + ii] : 0.f;
+    t2[ty + r][tx] = ok ? g2[(int64_t)jj * b + ii] : 0.f;
+    tb[ty + r][tx] = ok ? gbb[(int64_t)jj * b + ii] : 0.f;
+    tp[ty + r][tx] = ok ? gpp[(int64_t)jj * b + ii] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 32; r += 8) {
+    const int ii = i0 + ty + r, jj = j0 + tx;
+    if (ii < b && jj < b) {
+      const int64_t src = (int64_t)ii * b + jj, dst = (int64_t)ii * 2 * b + jj;
+      xb[dst] = g1[src] + t2[tx][ty + r];
+      xb[dst + b] = gbb[src] + tb[tx][ty + r];
+      xp[dst] = t1[tx][ty + r] + g2[src];
+      xp[dst + b] = gpp[src] + tp[tx][ty + r];
+    }
+  }
+}
+
+// LabLoss row i: s[i,:] = cos(brand_i, brand_:) -> partial[i] = sum_j exp(s_ij with the diagonal set to 0);
+// s[i,j] <- d loss / d s[i,j] = exp(s_ij) / b off the diagonal, 0 on it (masked_fill, loss.py:59-60).
+__global__ void __launch_bounds__(256) lab_row_kernel(float* __restrict__ s, int b, float* __restrict__ partial) {
+  __shared__ float red[8];
+  const int i = blockIdx.x;
+  float* row = s + (int64_t)i * b;
+  const float inv_b = 1.0f / (float)b;
+  float acc = 0.f;
+  for (int j = threadIdx.x; j < b; j += blockDim.x) {
+    const float e = j == i ? 1.0f : expf(row[j]);
+    acc += e;
+    row[j] = j == i ? 0.f : e * inv_b;
+  }
+  acc = block_sum_float(acc, red);
+  if (threadIdx.x == 0) partial[i] = acc;
+}
+
+// out = (sum(partial) - offset) * scale
+__global__ void __launch_bounds__(256) reduce_offset_kernel(const float* __restrict__ partial, int n, double offset, double scale,
+                                                             float* __restrict__ out) {
+  __shared__ double red[8];
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += (double)partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    out[0] = (float)((t - offset) * scale);
+  }
+}
+
+// x / ||x|| without the eps clamp (loss.l2norm, loss.py:20-24); norm_out optional
+__global__ void __launch_bounds__(256) l2norm_rows_kernel(const float* __restrict__ x, int d, float* __restrict__ y,
+                                                           float* __restrict__ norm_out) {
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) { const float v = x[(int64_t)r * d + c]; ss += v * v; }
+  ss = block_sum_float(ss, red);
+  const float nrm = sqrtf(ss);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) y[(int64_t)r * d + c] = x[(int64_t)r * d + c] / nrm;
+  if (norm_out && threadIdx.x == 0) norm_out[r] = nrm;
+}
+
 }  // namespace frx
 
 extern "C" {
@@ -427,6 +566,118 @@ int frx_contrastive_fwd_bwd(const float* brand, const float* post, int b, int d,
     }
     normalize_bwd_kernel<<<b, 256, 0, st>>>(dbn, bn, nrm_b, d, d_brand);
     normalize_bwd_kernel<<<b, 256, 0, st>>>(dpn_src, pn, nrm_p, d, d_post);
+  }
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
+size_t frx_crossclr_workspace_bytes(int b, int d) {
+  if (b <= 0 || d <= 0) return 0;
+  return 5 * frx::align256((size_t)b * b * 4) + 2 * frx::align256((size_t)b * 2 * b * 4) + 6 * frx::align256((size_t)b * d * 4) +
+         6 * frx::align256((size_t)b * 4) + frx::tc_scratch_bytes(b, d, 2 * b) + 256;
+}
+
+int frx_crossclr_fwd_bwd(const float* brand, const float* post, int b, int d, float temperature, float negative_weight,
+                         int mean_style, float* loss, float* d_brand, float* d_post, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(brand && post && loss, "frx_crossclr_fwd_bwd: NULL pointer");
+  FRX_CHECK_ARG(b > 0 && d > 0, "frx_crossclr_fwd_bwd: bad sizes");
+  FRX_CHECK_ARG((d_brand == nullptr) == (d_post == nullptr), "frx_crossclr_fwd_bwd: gradients go together");
+  const size_t need = frx_crossclr_workspace_bytes(b, d);
+  if (!workspace || workspace_bytes < need) {
+    set_error("frx_crossclr_fwd_bwd: workspace %zu bytes, need %zu", workspace_bytes, need);
+    return FRX_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+  auto take = [&](size_t bytes) { float* p = reinterpret_cast<float*>(w); w += align256(bytes); return p; };
+  const size_t bb4 = (size_t)b * b * 4, bd4 = (size_t)b * d * 4;
+  float* lbp = take(bb4); float* lbb = take(bb4); float* lpp = take(bb4); float* g1 = take(bb4); float* g2 = take(bb4);
+  float* xb = take(2 * bb4); float* xp = take(2 * bb4);
+  float* n1 = take(2 * bd4);      // [pn ; bn]   (2b x d)
+  float* n2 = take(2 * bd4);      // [bn ; pn]
+  float* dbn = take(bd4); float* dpn = take(bd4);
+  float* rank_p = take((size_t)b * 4); float* rank_b = take((size_t)b * 4); float* diag = take((size_t)b * 4);
+  float* partial = take((size_t)b * 4); float* nrm_b = take((size_t)b * 4); float* nrm_p = take((size_t)b * 4);
+  TcScratch ts;
+  ts.xa = reinterpret_cast<float*>(w); w += xa_bytes(b, d, 2 * b);
+  ts.yb = reinterpret_cast<float*>(w); w += yb_bytes(b, d, 2 * b);
+  ts.ksplit = w;
+  ts.ksplit_bytes = ks_bytes(b);
+  const bool tc = tc_ok(b, b, d) && b % 4 == 0;
+  const float inv_t = 1.0f / temperature;
+  const float scale = mean_style ? 0.5f / (float)b : 0.5f;
+  float* pn = n1; float* bn = n1 + (size_t)b * d;
+  // rank weights from the RAW tile scores[i][j] = post_i . brand_j (loss_ctrs.py:62-77)
+  int rc = gemm_nt(st, tc, ts, post, false, d, brand, false, d, lbp, b, b, b, d, 1.f);
+  if (rc) return rc;
+  tile_rank_kernel<<<b, 128, 0, st>>>(lbp, b, rank_p, rank_b, diag);
+  normalize_rows_kernel<<<b, 256, 0, st>>>(post, d, pn, nrm_p);
+  normalize_rows_kernel<<<b, 256, 0, st>>>(brand, d, bn, nrm_b);
+  FRX_CUDA(cudaMemcpyAsync(n2, bn, bd4, cudaMemcpyDeviceToDevice, st));
+  FRX_CUDA(cudaMemcpyAsync(n2 + (size_t)b * d, pn, bd4, cudaMemcpyDeviceToDevice, st));
+  rc = gemm_nt(st, tc, ts, bn, false, d, pn, false, d, lbp, b, b, b, d, inv_t);
+  if (rc) return rc;
+  rc = gemm_nt(st, tc, ts, bn, false, d, bn, false, d, lbb, b, b, b, d, inv_t);
+  if (rc) return rc;
+  rc = gemm_nt(st, tc, ts, pn, false, d, pn, false, d, lpp, b, b, b, d, inv_t);
+  if (rc) return rc;
+  crossclr_row_kernel<<<b, 256, 0, st>>>(lbp, lbb, lpp, b, negative_weight, scale, rank_p, rank_b, g1, g2, partial);
+  reduce_partials_kernel<<<1, 256, 0, st>>>(partial, b, scale, loss);
+  if (d_post) {
+    dim3 cg((b + 31) / 32, (b + 31) / 32);
+    crossclr_combine_kernel<<<cg, 256, 0, st>>>(g1, g2, lbb, lpp, b, xb, xp);
+    const bool tc2 = tc && (2 * b) % 4 == 0;
+    rc = gemm_nt(st, tc2, ts, xb, false, 2 * b, n1, true, d, dbn, d, b, d, 2 * b, inv_t);   // d_bn = [G_bp | G_bb+G_bb^T] . [pn ; bn] / T
+    if (rc) return rc;
+    rc = gemm_nt(st, tc2, ts, xp, false, 2 * b, n2, true, d, dpn, d, b, d, 2 * b, inv_t);   // d_pn = [G_bp^T | G_pp+G_pp^T] . [bn ; pn] / T
+    if (rc) return rc;
+    normalize_bwd_kernel<<<b, 256, 0, st>>>(dbn, bn, nrm_b, d, d_brand);
+    normalize_bwd_kernel<<<b, 256, 0, st>>>(dpn, pn, nrm_p, d, d_post);
+  }
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
+size_t frx_lab_workspace_bytes(int b, int d) {
+  if (b <= 0 || d <= 0) return 0;
+  return frx::align256((size_t)b * b * 4) + 2 * frx::align256((size_t)b * d * 4) + 2 * frx::align256((size_t)b * 4) +
+         frx::tc_scratch_bytes(b, d, b) + 256;
+}
+
+int frx_lab_fwd_bwd(const float* brand, int b, int d, float* loss, float* d_brand, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(brand && loss, "frx_lab_fwd_bwd: NULL pointer");
+  FRX_CHECK_ARG(b > 0 && d > 0, "frx_lab_fwd_bwd: bad sizes");
+  const size_t need = frx_lab_workspace_bytes(b, d);
+  if (!workspace || workspace_bytes < need) {
+    set_error("frx_lab_fwd_bwd: workspace %zu bytes, need %zu", workspace_bytes, need);
+    return FRX_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+  auto take = [&](size_t bytes) { float* p = reinterpret_cast<float*>(w); w += align256(bytes); return p; };
+  float* s = take((size_t)b * b * 4);
+  float* bn = take((size_t)b * d * 4); float* dbn = take((size_t)b * d * 4);
+  float* partial = take((size_t)b * 4); float* nrm = take((size_t)b * 4);
+  TcScratch ts;
+  ts.xa = reinterpret_cast<float*>(w); w += xa_bytes(b, d, b);
+  ts.yb = reinterpret_cast<float*>(w); w += yb_bytes(b, d, b);
+  ts.ksplit = w;
+  ts.ksplit_bytes = ks_bytes(b);
+  const bool tc = tc_ok(b, b, d) && b % 4 == 0;
+  l2norm_rows_kernel<<<b, 256, 0, st>>>(brand, d, bn, nrm);
+  int rc = gemm_nt(st, tc, ts, bn, false, d, bn, false, d, s, b, b, b, d, 1.f);           // cosine_sim(brand, brand)
+  if (rc) return rc;
+  lab_row_kernel<<<b, 256, 0, st>>>(s, b, partial);
+  reduce_offset_kernel<<<1, 256, 0, st>>>(partial, b, (double)b, 1.0 / (double)b, loss);   // (sum exp(s) - B) / B
+  if (d_brand) {
+    // s is symmetric, so is G = d loss / d s: d_bn = (G + G^T) . bn = 2 G . bn
+    rc = gemm_nt(st, tc, ts, s, false, b, bn, true, d, dbn, d, b, d, b, 2.f);
+    if (rc) return rc;
+    normalize_bwd_kernel<<<b, 256, 0, st>>>(dbn, bn, nrm, d, d_brand);
   }
   FRX_LAUNCH_CHECK();
   return FRX_OK;

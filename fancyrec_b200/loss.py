@@ -3,8 +3,9 @@
   TripletLoss   loss.py:67-143   forward + backward fused on the device (frx_triplet_fwd_bwd): the B x B
                                  tile, rank weights, hinge, same-brand mask and dS are produced without the B
                                  GEMV launches, four sorts and B^2 host loop of the reference.
-  LabLoss / cosine_sim / order_sim / euclidean_sim / l2norm: same formulas on torch device ops
-                                 (not on the hot path north_star names).
+  LabLoss       loss.py:55-63    forward + backward fused on the device (frx_lab_fwd_bwd).
+  cosine_sim / order_sim / euclidean_sim / l2norm: same formulas on torch device ops (helpers the reference's
+                                 TripletLoss stores but never calls, loss.py:78-85).
 As in the reference, `max_violation`, `measure` and `loss_fun` are accepted and do not change the
 result (loss.py:85 vs :87-143), and `direction != 'all'` raises TypeError (loss.py:131-132).
 """
@@ -37,15 +38,28 @@ def euclidean_sim(im, s):
     return -YmX.pow(2).sum(2).t()
 
 
+class _LabFn(Function):
+    @staticmethod
+    def forward(ctx, brand_embs):
+        loss, d_brand = ops.lab_fwd_bwd(brand_embs, True)
+        ctx.save_for_backward(d_brand)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        d_brand, = ctx.saved_tensors
+        return d_brand * grad_out
+
+
 class LabLoss(nn.Module):
+    """loss.py:55-63 fused on the device (frx_lab_fwd_bwd): cosine Gram tile on the tensor cores (3xTF32),
+    exp / masked sum and the gradient tile in one row kernel."""
+
     def __init__(self):
         super(LabLoss, self).__init__()
 
     def forward(self, brand_embs):
-        s = cosine_sim(brand_embs, brand_embs)
-        eye = torch.eye(s.size(0), device=s.device) > .5
-        s = s.masked_fill(eye, 0)
-        return (torch.sum(torch.exp(s)) - s.size(0)) / s.size(0)
+        return _LabFn.apply(brand_embs.contiguous().float())
 
 
 class _TripletFn(Function):

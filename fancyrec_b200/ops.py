@@ -323,3 +323,35 @@ def contrastive_fwd_bwd(brand, post, keys, mask_col0, no_intra, temperature, neg
                                          ws.numel(), _stream(brand))
     _lib.check(rc, "frx_contrastive_fwd_bwd")
     return loss, d_brand, d_post
+
+
+def crossclr_fwd_bwd(brand, post, temperature, negative_weight, mean_style, want_grad=True):
+    lib = _lib.load()
+    _req(brand, torch.float32, "brand", 2)
+    _req(post, torch.float32, "post", 2)
+    b, d = brand.shape
+    dev = brand.device
+    ws = torch.empty(lib.frx_crossclr_workspace_bytes(b, d), dtype=torch.uint8, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    d_brand = torch.empty_like(brand) if want_grad else None
+    d_post = torch.empty_like(post) if want_grad else None
+    with torch.cuda.device(dev):
+        rc = lib.frx_crossclr_fwd_bwd(_ptr(brand), _ptr(post), b, d, float(temperature), float(negative_weight),
+                                      int(mean_style), _ptr(loss), _ptr(d_brand), _ptr(d_post), _ptr(ws), ws.numel(),
+                                      _stream(brand))
+    _lib.check(rc, "frx_crossclr_fwd_bwd")
+    return loss, d_brand, d_post
+
+
+def lab_fwd_bwd(brand, want_grad=True):
+    lib = _lib.load()
+    _req(brand, torch.float32, "brand", 2)
+    b, d = brand.shape
+    dev = brand.device
+    ws = torch.empty(lib.frx_lab_workspace_bytes(b, d), dtype=torch.uint8, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    d_brand = torch.empty_like(brand) if want_grad else None
+    with torch.cuda.device(dev):
+        rc = lib.frx_lab_fwd_bwd(_ptr(brand), b, d, _ptr(loss), _ptr(d_brand), _ptr(ws), ws.numel(), _stream(brand))
+    _lib.check(rc, "frx_lab_fwd_bwd")
+    return loss, d_brand

@@ -224,6 +224,23 @@ int frx_contrastive_fwd_bwd(const float* brand, const float* post, int b, int d,
 /* F.normalize(post) rows (eps 1e-12), what ContrastiveLoss enqueues (loss_ctrs.py:195,200). */
 int frx_normalize_rows(const float* x, int rows, int d, float* out, void* stream);
 
+/* A14  CrossCLR_onlyIntraModality (loss_ctrs.py:52-117), forward + backward.
+ *   Row and column rank weights from the raw tile post.brand^T (loss_ctrs.py:62-77); F.normalize both; four
+ *   B x B Gram matrices / T; the intra-modality logits * negative_weight with their diagonal entry multiplied to 0
+ *   (it stays in the soft-max as a logit of 0, loss_ctrs.py:97-104); loss = (sum|mean_b + sum|mean_p) / 2.
+ */
+size_t frx_crossclr_workspace_bytes(int b, int d);
+int frx_crossclr_fwd_bwd(const float* brand, const float* post, int b, int d,
+                         float temperature, float negative_weight, int mean_style,
+                         float* loss, float* d_brand, float* d_post,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* A14  LabLoss (loss.py:55-63): (sum exp(cos(brand_i, brand_j), diagonal filled with 0) - B) / B, forward + backward
+ *   (d_brand may be NULL).  Rows are normalised without an epsilon, as loss.l2norm does (loss.py:20-24). */
+size_t frx_lab_workspace_bytes(int b, int d);
+int frx_lab_fwd_bwd(const float* brand, int b, int d, float* loss, float* d_brand,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Measurement hook (bench.py roofline leg): when enabled, every MAIN launch of the fused score + top-k kernel
  * (not the sample pass, not dense / count launches) is bracketed by a pair of CUDA events on its own stream.  frx_probe_read synchronises

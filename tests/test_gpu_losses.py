@@ -140,3 +140,74 @@ def test_crossclr_lab_golden(golden_dir):
     val.backward()
     np.testing.assert_allclose(val.item(), g["lab_loss"], rtol=1e-5)
     np.testing.assert_allclose(bt.grad.cpu().numpy(), g["lab_dbrand"], rtol=1e-3, atol=1e-6)
+
+
+def _torch_crossclr(brand, post, t=0.03, w=0.8, style='sum'):
+    """Plain torch fp32 restatement of loss_ctrs.py:52-117 (rank weights by counting, ties to the smaller index)."""
+    import torch.nn.functional as F
+    b = brand.shape[0]
+    with torch.no_grad():
+        sc = post @ brand.t()
+        idx = torch.arange(b, device=sc.device)
+        dg = sc.diag()
+        lower = idx[None, :] < idx[:, None]
+        pos_r = (sc > dg[:, None]).sum(1) + ((sc == dg[:, None]) & lower).sum(1)
+        pos_c = (sc > dg[None, :]).sum(0) + ((sc == dg[None, :]) & lower.t()).sum(0)
+        rank_p = 1 / (b - (pos_r + 1).float() + 1) + 1
+        rank_b = 1 / (b - (pos_c + 1).float() + 1) + 1
+    bn, pn = F.normalize(brand, dim=1), F.normalize(post, dim=1)
+    off = 1 - torch.eye(b, device=brand.device)
+    bl = torch.cat([bn @ pn.t() / t, w * (bn @ bn.t() / t) * off], 1)
+    pl = torch.cat([pn @ bn.t() / t, w * (pn @ pn.t() / t) * off], 1)
+    lb = rank_b * -torch.log(F.softmax(bl, 1).diagonal())
+    lp = rank_p * -torch.log(F.softmax(pl, 1).diagonal())
+    return (lb.sum() + lp.sum()) / 2 if style == 'sum' else (lb.mean() + lp.mean()) / 2
+
+
+@pytest.mark.parametrize("b,d,style", [(512, 1024, 'sum'), (512, 3072, 'mean'), (96, 200, 'sum'), (33, 50, 'mean')])
+def test_crossclr_config3_vs_oracle_and_torch(b, d, style):
+    """Fused CrossCLR at the config-3 batch: value vs the fp64 oracle, gradients vs torch fp32 autograd of the
+    same formula (tolerances as for the other loss tiles: value rtol 2e-4, gradients 2e-3 of the largest entry)."""
+    from fancyrec_b200 import loss_ctrs as fctrs
+    rs = np.random.RandomState(b + d)
+    brand = rs.standard_normal((b, d)).astype(np.float32)
+    post = (rs.standard_normal((b, d)) + 0.1 * brand).astype(np.float32)     # weakly aligned: the loss stays O(1)
+    bt, pt = to_dev(brand).requires_grad_(), to_dev(post).requires_grad_()
+    val = fctrs.CrossCLR_onlyIntraModality(cost_style=style).to(dev())(bt, pt)
+    val.backward()
+    np.testing.assert_allclose(val.item(), oloss.crossclr_loss(brand, post, cost_style=style), rtol=2e-4)
+    br, pr = to_dev(brand).requires_grad_(), to_dev(post).requires_grad_()
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = _torch_crossclr(br, pr, style=style)
+        ref.backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    np.testing.assert_allclose(val.item(), ref.item(), rtol=2e-4)
+    for got, want in ((bt.grad, br.grad), (pt.grad, pr.grad)):
+        want = want.cpu().numpy()
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-3, atol=2e-3 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("b,d", [(512, 1024), (52, 2048), (33, 50)])
+def test_lab_loss_vs_oracle_and_torch(b, d):
+    from fancyrec_b200 import loss as floss
+    rs = np.random.RandomState(b * 3 + d)
+    brand = rs.standard_normal((b, d)).astype(np.float32)
+    bt = to_dev(brand).requires_grad_()
+    val = floss.LabLoss()(bt)
+    val.backward()
+    np.testing.assert_allclose(val.item(), oloss.lab_loss(brand), rtol=1e-5)
+    br = to_dev(brand).requires_grad_()
+    n = br / br.pow(2).sum(1, keepdim=True).sqrt()
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sref = (n @ n.t()).masked_fill(torch.eye(b, device=br.device) > .5, 0)
+        ref = (torch.exp(sref).sum() - b) / b
+        ref.backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    want = br.grad.cpu().numpy()
+    np.testing.assert_allclose(bt.grad.cpu().numpy(), want, rtol=2e-3, atol=2e-3 * np.abs(want).max())
