@@ -29,6 +29,7 @@ SIGNATURES = {
                                     c_vp, c_i64, c_vp, c_sz, c_vp]),
     "frx_score_dense_tf32": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "frx_score_count_tf32": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "frx_softmax_pool": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "frx_split_tf32x3": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp]),
     "frx_topk_merge": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
     "frx_label_stats": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),

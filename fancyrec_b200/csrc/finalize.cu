@@ -631,6 +631,70 @@ __global__ void __launch_bounds__(256) split_rows_vec_kernel(const float* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Masked soft-max weighted pool: the per-sample loop of MultiHeadSelfAttention.forward
+// (model.py:105-114)  weight[i, :len_i] = softmax(atten[i, :len_i]);  out = (weight * x).mean(dim=1)
+// as one pass: block b soft-maxes its <= T logits in shared memory, then every thread accumulates its columns over
+// the valid steps only (padded steps are never read).  The mean runs over the PADDED length T, as the reference's does.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_pool_kernel(const float* __restrict__ x, const float* __restrict__ logit,
+                                                            const int64_t* __restrict__ lengths, int t_max, int d,
+                                                            float* __restrict__ out) {
+  extern __shared__ float wgt[];                 // [t_max]
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  int64_t len64 = lengths[b];
+  const int len = len64 < 0 ? 0 : (len64 > t_max ? t_max : (int)len64);
+  const float* lg = logit + (int64_t)b * t_max;
+  float m = -INFINITY;
+  for (int t = threadIdx.x; t < len; t += blockDim.x) m = fmaxf(m, lg[t]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  for (int w = 0; w < 8; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float z = 0.f;
+  for (int t = threadIdx.x; t < len; t += blockDim.x) { const float e = expf(lg[t] - m); wgt[t] = e; z += e; }
+  z = warp_sum(z);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = z;
+  __syncthreads();
+  z = 0.f;
+  for (int w = 0; w < 8; ++w) z += red[w];
+  const float inv = 1.0f / (z * (float)t_max);
+  const float* xb = x + (int64_t)b * t_max * d;
+  float* ob = out + (int64_t)b * d;
+  if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int t = 0;
+      for (; t + 4 <= len; t += 4) {               // four independent 128-bit loads in flight
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(xb + (int64_t)(t + u) * d + c));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float w = wgt[t + u];
+          acc.x = fmaf(w, v[u].x, acc.x); acc.y = fmaf(w, v[u].y, acc.y);
+          acc.z = fmaf(w, v[u].z, acc.z); acc.w = fmaf(w, v[u].w, acc.w);
+        }
+      }
+      for (; t < len; ++t) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(xb + (int64_t)t * d + c));
+        const float w = wgt[t];
+        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+      }
+      *reinterpret_cast<float4*>(ob + c) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    }
+  } else {
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      float acc = 0.f;
+      for (int t = 0; t < len; ++t) acc = fmaf(wgt[t], xb[(int64_t)t * d + c], acc);
+      ob[c] = acc * inv;
+    }
+  }
+}
+
 void launch_split_rows(const float* x, const int64_t* ids, int rows, int cols, int64_t ld_x, float scale, int pattern,
                        float* out, cudaStream_t st) {
   split_rows_kernel<<<rows, 256, 0, st>>>(x, ids, cols, ld_x, scale, pattern, out);
@@ -700,6 +764,24 @@ int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_
     if (smem > 48 * 1024) FRX_CUDA(cudaFuncSetAttribute(finalize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     finalize_kernel<1><<<grid, kFinThreads, smem, st>>>(P);
   }
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
+int frx_softmax_pool(const float* x, const float* logits, const int64_t* lengths, int batch, int t_max, int d, float* out,
+                     void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(x && logits && lengths && out, "frx_softmax_pool: NULL pointer");
+  FRX_CHECK_ARG(batch >= 0 && t_max > 0 && d > 0, "frx_softmax_pool: bad sizes batch=%d t_max=%d d=%d", batch, t_max, d);
+  FRX_CHECK_ARG((size_t)t_max * sizeof(float) <= 160 * 1024, "frx_softmax_pool: t_max = %d exceeds 40960 steps", t_max);
+  int dev = 0;
+  FRX_CUDA(cudaGetDevice(&dev));
+  int rc = frx_device_check(dev);
+  if (rc) return rc;
+  if (batch == 0) return FRX_OK;
+  const size_t smem = (size_t)t_max * sizeof(float);
+  if (smem > 48 * 1024) FRX_CUDA(cudaFuncSetAttribute(softmax_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  softmax_pool_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(x, logits, lengths, t_max, d, out);
   FRX_LAUNCH_CHECK();
   return FRX_OK;
 }

@@ -87,6 +87,25 @@ def masked_mean_pool(x, lengths, l2norm=False):
                           want_f32=True, want_bf16=False)[0]
 
 
+def masked_softmax_pool(x, logits, lengths):
+    """MultiHeadSelfAttention's weighting step (model.py:105-114) without the per-sample Python loop:
+    x [B, T, D] fp32, logits [B, T] or [B, T, 1] fp32 (head-averaged attention scores), lengths [B] ->
+    out[b] = mean over the padded T of softmax(logits[b, :len_b]) * x[b]  ([B, D] fp32)."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x", 3)
+    b, t, d = x.shape
+    logits = logits.reshape(b, t)
+    _req(logits, torch.float32, "logits", 2)
+    lengths = torch.as_tensor(lengths, device=x.device).to(torch.int64).contiguous()
+    if lengths.numel() != b:
+        raise ValueError("lengths has %d entries, expected %d" % (lengths.numel(), b))
+    out = torch.empty((b, d), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.frx_softmax_pool(_ptr(x), _ptr(logits), _ptr(lengths), b, t, d, _ptr(out), _stream(x))
+    _lib.check(rc, "frx_softmax_pool")
+    return out
+
+
 def split_tf32x3(x, side):
     """fp32 [N, D] -> the K-concatenated 3xTF32 operand [N, 3D] (side 0 = brand: [hi|lo|hi]; side 1 = post:
     [hi|hi|lo]).  score_*(a3, b3, d=3D) on these gives fp32-grade scores on the tf32 tensor-core path."""

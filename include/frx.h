@@ -132,6 +132,13 @@ int frx_score_count(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* po
                     const float* thr_score, const int32_t* thr_index,
                     unsigned long long* count_out, void* stream);
 
+/* Masked soft-max weighted pool (MultiHeadSelfAttention.forward, model.py:105-114, without its per-sample loop):
+ *   out[b, :] = (1 / t_max) * sum_{t < lengths[b]} softmax(logits[b, :lengths[b]])[t] * x[b, t, :]
+ * x [batch, t_max, d] fp32, logits [batch, t_max] fp32 (the head-averaged attention scores), lengths [batch] int64
+ * (clamped to 0..t_max; a zero length gives a zero row), out [batch, d] fp32.  One HBM pass over the valid steps. */
+int frx_softmax_pool(const float* x, const float* logits, const int64_t* lengths, int batch, int t_max, int d,
+                     float* out, void* stream);
+
 /* 3xTF32 operands (fp32-grade scores on the tensor cores, the mode that meets the 1e-5 score tolerance):
  * x = hi + lo with hi, lo exactly representable in tf32; the K-concatenated operands
  *   brand side (side 0): [hi | lo | hi]      post side (side 1): [hi | hi | lo]        (each [rows, 3 * cols] fp32)

@@ -256,3 +256,83 @@ def test_masked_mean_pool_matches_reference_loop():
     np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-6)
     gotn = ops.masked_mean_pool(to_dev(x), to_dev(lengths), l2norm=True).cpu().numpy()
     np.testing.assert_allclose(gotn, want / np.linalg.norm(want, axis=1, keepdims=True), rtol=RTOL, atol=1e-6)
+
+
+def test_masked_softmax_pool_matches_reference_loop():
+    """MultiHeadSelfAttention.forward's per-sample soft-max loop + weighted mean (model.py:105-114)
+    as one pass; compared with the loop itself restated in fp64."""
+    from fancyrec_b200 import ops
+    rs = np.random.RandomState(29)
+    for b, t, d in ((17, 64, 2048), (5, 7, 50), (3, 300, 128)):
+        x = rs.standard_normal((b, t, d)).astype(np.float32)
+        att = (3 * rs.standard_normal((b, t, 1))).astype(np.float32)
+        lengths = rs.randint(1, t + 1, b)
+        lengths[0], lengths[1] = t, 1
+        got = ops.masked_softmax_pool(to_dev(x), to_dev(att), lengths.tolist()).cpu().numpy()
+        want = np.zeros((b, d))
+        for i in range(b):
+            a = att[i, :lengths[i], 0].astype(np.float64)
+            w = np.exp(a - a.max()); w /= w.sum()
+            weight = np.zeros(t); weight[:lengths[i]] = w
+            want[i] = (weight[:, None] * x[i].astype(np.float64)).mean(0)
+        np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-7)   # expf + fp32 weighted sums vs fp64
+
+
+def test_validate_and_tester_flow(golden_dir, capsys, tmp_path):
+    """trainer.validate / tester.evaluate on the exact-lattice fixture through a fake loader: the 8 metrics are
+    bit-identical to the UNMODIFIED reference run stored in the golden file, rsum follows trainer.py:413-415, the
+    printed lines are the reference's, and save_checkpoint keeps the reference's selection rule."""
+    from fancyrec_b200 import tester, trainer
+    g = np.load(os.path.join(golden_dir, "ranking_lattice.npz"))
+    nb, lab, w, e, posts = synth.ranking_inputs("lattice")
+    mdl = _fake_model(nb, w, e)
+    d = posts.shape[1]
+    mdl.opt = types.SimpleNamespace(single_modal_text=False, single_modal_visual=False, common_embedding_size=d,
+                                    brand_num=nb, metric='auc', log_step=100)
+
+    class _Enc(torch.nn.Module):
+        def forward(self, x):
+            return x
+    mdl.vid_encoding = mdl.text_encoding = mdl.fusion_encoding = _Enc()
+
+    class _Callable:
+        """model(brand_ids, videos, captions) -> (None, post embeddings); attribute access falls through to mdl."""
+        def __call__(self, brand_ids, videos, captions):
+            return None, videos.to(dev())
+
+        def __getattr__(self, name):
+            return getattr(mdl, name)
+
+    n = posts.shape[0]
+    posts_t, lab_t = torch.from_numpy(posts), torch.from_numpy(lab)
+
+    class _Loader:
+        dataset = list(range(n))
+
+        def __iter__(self):
+            for lo in range(0, n, 128):
+                idxs = list(range(lo, min(n, lo + 128)))
+                yield lab_t[idxs], posts_t[idxs], None, idxs, None, None
+
+        def __len__(self):
+            return (n + 127) // 128
+
+    out = trainer.validate(mdl.opt, _Loader(), _Callable())
+    printed = capsys.readouterr().out.splitlines()
+    medr, meanr, auc, n10, n50, r1, r5, r10 = tuple(g["result_stable"])
+    assert tuple(float(x) for x in out[1:]) == (auc, n10, n50, medr, meanr, r1, r5, r10)
+    assert float(out[0]) == float((np.float64(auc) + np.float64(n10) + np.float64(n50)) * 100 + r1 + r5 + r10)
+    assert [l.split(':')[0] for l in printed] == ['MedR', 'MeanR', 'AUC[0-1]', 'NDCG@10[0-1]', 'NDCG@50[0-1]',
+                                                  'recall@1', 'recall@5', 'recall@10']
+    res = tester.evaluate(mdl.opt, _Callable(), _Loader(), log_step=100)
+    assert tuple(float(x) for x in res) == tuple(g["result_stable"])
+    assert len(capsys.readouterr().out.splitlines()) == 4
+    # checkpoint selection (trainer.py:419-424)
+    prefix = str(tmp_path) + os.sep
+    best = trainer.save_checkpoint({"x": 1}, 10.0, 0.0, prefix=prefix, best_epoch=None)
+    assert best == 10.0 and os.path.exists(prefix + 'model_best.pth.tar')
+    os.remove(prefix + 'checkpoint.pth.tar')
+    assert trainer.save_checkpoint({"x": 2}, 9.5, best, prefix=prefix, best_epoch=1) == 10.0
+    assert not os.path.exists(prefix + 'checkpoint.pth.tar')          # more than 1 % below the best: not saved
+    assert trainer.save_checkpoint({"x": 3}, 9.95, best, prefix=prefix, best_epoch=1) == 10.0
+    assert os.path.exists(prefix + 'checkpoint.pth.tar')
