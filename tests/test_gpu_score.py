@@ -157,6 +157,47 @@ def test_tf32x3_through_public_api(monkeypatch):
     assert np.array_equal(stats["auc_num"], oref.rank_stats(ours, lab)["auc_num"])
 
 
+@pytest.mark.parametrize("kind", ["ascending", "descending", "constant", "two_level", "negative", "sparse_nonneg"])
+@pytest.mark.parametrize("k", [64, 1000])
+def test_adversarial_orders_large_np(kind, k):
+    """Worst cases for the threshold machinery (sample-seeded thresholds + the shared per-row candidate histogram):
+    scores that keep improving along the post axis (every tile beats everything before it), scores that only get
+    worse, one constant score (every post ties), two score levels, all-negative scores, and sparse non-negative
+    rows whose sample threshold is exactly 0.  The result must still be the exact top-k of our own score tile."""
+    nb, npost, d = 33, 400000, 64
+    rs = np.random.RandomState(len(kind) + k)
+    brand = np.zeros((nb, d), np.float32)
+    brand[:, 0] = 1.0
+    brand[:, 1:] = 0.05 * rs.standard_normal((nb, d - 1))
+    posts = 0.05 * rs.standard_normal((npost, d)).astype(np.float32)
+    ramp = np.linspace(0.1, 3.0, npost, dtype=np.float32)
+    if kind == "ascending":
+        posts[:, 0] = ramp
+    elif kind == "descending":
+        posts[:, 0] = ramp[::-1]
+    elif kind == "constant":
+        posts[:] = 0.0
+        posts[:, 0] = 1.0
+        brand[:, 1:] = 0.0
+    elif kind == "two_level":
+        posts[:] = 0.0
+        posts[:, 0] = 1.0
+        posts[::1000, 1] = 1.0                                       # every 1000th post scores lower
+        brand[:, 1:] = 0.0
+    elif kind == "negative":
+        posts[:, 0] = -ramp
+    else:
+        posts = np.abs(posts) * (rs.random_sample((npost, d)) < 0.02)    # most dot products are exactly 0
+        posts[:, 1] += 1e-3                                              # no zero rows
+        brand = np.abs(brand)
+    lab = synth.labels(17, npost, nb)
+    res, dense, _, _ = _dense_and_topk(brand, posts.astype(np.float32), k, labels=lab, index_base=3)
+    want = oref.topk_indices(dense, k)
+    assert np.array_equal(res["index"].cpu().numpy(), want + 3)
+    assert np.array_equal(res["scores"].cpu().numpy(), np.take_along_axis(dense, want, 1))
+    assert np.array_equal(res["pos_score"].cpu().numpy(), dense[lab, np.arange(npost)])
+
+
 def test_heavy_ties_and_index_base():
     """Quantised scores (few distinct values) -> the tie-break carries the whole ranking."""
     rs = np.random.RandomState(3)

@@ -8,7 +8,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-nb, n, d, k = 300, 200003, 256, 100
+nb, n, d, k = [int(v) for v in (sys.argv[1].split(",") if len(sys.argv) > 1 else "300,200003,256,100".split(","))]
 g = torch.Generator(device="cpu").manual_seed(5)
 brand = torch.randn(nb, d, generator=g)
 posts = torch.randn(n, d, generator=g)
