@@ -327,38 +327,18 @@ def run_e2e(ev, w, e, labels, visual, text, args, dev, world):
     h_labels = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
     h_visual.copy_(visual); h_text.copy_(text); h_labels.copy_(labels)
     torch.cuda.synchronize()
-    chunk = 131072
-    copy_stream = torch.cuda.Stream(device=dev)
+    from fancyrec_b200 import ingest
     ld = ops.round_up(ev.d, 64)
     post_op = torch.empty((n_local, ld), dtype=torch.bfloat16, device=dev)
-    stage_v = [torch.empty((chunk, dv), device=dev) for _ in range(2)]
-    stage_t = [torch.empty((chunk, dt), device=dev) for _ in range(2)]
     d_labels = torch.empty(n_local, dtype=torch.int32, device=dev)
-    lib = ev.lib
 
     def step():
-        main = torch.cuda.current_stream(dev)
         brand = ops.brand_embed(w, e, nb=ev.nb)
         brand_op = ops.finalize_posts(brand, final_norm=True)[1]
-        done = []
-        with torch.cuda.stream(copy_stream):
-            d_labels.copy_(h_labels, non_blocking=True)
-        free_ev = [None, None]
-        for ci, lo in enumerate(range(0, n_local, chunk)):
-            hi = min(n_local, lo + chunk)
-            s = ci & 1
-            with torch.cuda.stream(copy_stream):
-                if free_ev[s] is not None:
-                    copy_stream.wait_event(free_ev[s])        # staging buffer still being finalised
-                stage_v[s][:hi - lo].copy_(h_visual[lo:hi], non_blocking=True)
-                stage_t[s][:hi - lo].copy_(h_text[lo:hi], non_blocking=True)
-                ready = torch.cuda.Event(); ready.record(copy_stream)
-            main.wait_event(ready)
-            rc = lib.frx_finalize_posts(stage_v[s].data_ptr(), 0, 0, stage_t[s].data_ptr(), hi - lo, dv, dt, 7, 0,
-                                        post_op[lo:hi].data_ptr(), ld, main.cuda_stream)
-            assert rc == 0
-            free_ev[s] = torch.cuda.Event(); free_ev[s].record(main)
-        main.wait_stream(copy_stream)
+        d_labels.copy_(h_labels, non_blocking=True)
+        # pinned host rows -> chunked H2D on a copy stream, overlapped with the finalisation of the previous chunk
+        ingest.finalize_from_host(h_visual, h_text, visual_norm=True, text_norm=True, final_norm=True,
+                                  out_bf16=post_op, device=dev, chunk_posts=131072)
         st = ev.sharded.sharded_rank_statistics(brand_op, post_op, d_labels, ev.d, ev.cfg["k"], ev.n_total,
                                                 workspace=ev.workspace)
         stats = ev.ranking.host_statistics(st, ev.n_total, want_auc=False)
@@ -380,8 +360,9 @@ def run_e2e(ev, w, e, labels, visual, text, args, dev, world):
     d2h = ev.nb * (4 + 4 + 8 + 8 + 1)
     return {"value": pairs / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "api": "brand_embed + finalize_posts (pinned host -> device, chunked) + sharded_rank_statistics + "
-                   "host aggregate; same call chain as evaluator.test_post_ranking"}
+            "api": "ops.brand_embed + ingest.finalize_from_host (pinned host -> device, chunked, overlapped) + "
+                   "sharded.sharded_rank_statistics + ranking.aggregate; same call chain as "
+                   "evaluator.test_post_ranking"}
 
 
 # ---------------------------------------------------------------------------------------------

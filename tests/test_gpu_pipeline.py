@@ -242,6 +242,44 @@ def test_bigfile_ingest_to_device(tmp_path):
     np.testing.assert_allclose(out, np.array(want), rtol=RTOL, atol=1e-7)
 
 
+@pytest.mark.parametrize("chunk", [7, 64, 100000])
+def test_ingest_from_host_bit_identical_to_device_path(tmp_path, chunk):
+    """ingest.finalize_from_host (memmap / NumPy / pinned host features, chunked + double-buffered H2D) gives
+    bit for bit what ops.finalize_posts gives on device-resident inputs: pooled + scattered rows (feature.bin),
+    pooled + contiguous rows, and un-pooled visual + text rows."""
+    from fancyrec_b200 import ingest, ops
+    from fancyrec_b200.util.imgbigfile import ImageBigFile
+    rs = np.random.RandomState(31)
+    n_rows, dims = 900, 2048
+    feats = np.maximum(rs.standard_normal((n_rows, dims)), 0).astype(np.float32)
+    names = ["v%d_frame_%d" % (i // 9, i % 9) for i in range(n_rows)]
+    perm = rs.permutation(n_rows)
+    feats[perm].tofile(os.path.join(str(tmp_path), "feature.bin"))
+    open(os.path.join(str(tmp_path), "id.txt"), "w", encoding="utf8").write("#".join(names[i] for i in perm))
+    open(os.path.join(str(tmp_path), "shape.txt"), "w").write("%d %d" % (n_rows, dims))
+    bf = ImageBigFile(str(tmp_path))
+    posts = [[n for n in names[v * 9:(v + 1) * 9]][:1 + (v % 9)] for v in range(n_rows // 9)]     # 1..9 frames
+    row_idx, row_ptr = bf.read_csr(posts)
+    text = rs.standard_normal((len(posts), 300)).astype(np.float32)
+    kw = dict(visual_norm=True, text_norm=True, final_norm=True, want_f32=True, want_bf16=True)
+    want = ops.finalize_posts(to_dev(np.array(bf.matrix)), to_dev(text), row_ptr=to_dev(row_ptr),
+                              row_idx=to_dev(row_idx), **kw)
+    got = ingest.finalize_from_host(bf.matrix, text, row_ptr=row_ptr, row_idx=row_idx, chunk_posts=chunk, **kw)
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    # contiguous rows per post (no gather list), pinned source
+    gathered = torch.from_numpy(np.array(bf.matrix)[row_idx]).pin_memory()
+    got = ingest.finalize_from_host(gathered, torch.from_numpy(text), row_ptr=row_ptr, chunk_posts=chunk, **kw)
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    # one row per post + text
+    vis = rs.standard_normal((len(posts), 1024)).astype(np.float32)
+    want = ops.finalize_posts(to_dev(vis), to_dev(text), **kw)
+    got = ingest.finalize_from_host(torch.from_numpy(vis).pin_memory(), torch.from_numpy(text).pin_memory(),
+                                    chunk_posts=chunk, **kw)
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    got = ingest.finalize_from_host(vis, None, chunk_posts=chunk, final_norm=True, want_bf16=True)
+    assert torch.equal(got[1], ops.finalize_posts(to_dev(vis), final_norm=True)[1]) and got[0] is None
+
+
 def test_masked_mean_pool_matches_reference_loop():
     """the encoders' per-sample `torch.mean(seq[:len], 0)` loops (model.py:105-114) as one
     pass of the pooling kernel."""
