@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("FRX_CLOCK_MS", "50")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -170,7 +170,8 @@ class Evaluator:
         self.workspace = st["workspace"]
         # brand_embed, 2 x finalize | sample pass: dense score + row k-th select | main: score + merge | label_stats,
         # decode_best, rank_from_topk (+ merge_lists when sharded, + count pass when a first positive is deep)
-        self.launches = 3 + 2 + 2 + 3 + (1 if self.world > 1 else 0) + (1 if st["count_pass"] else 0)
+        # ... missing_thresholds, score_count (returns at once unless a first positive is missing), pack_rank_stats
+        self.launches = 3 + 2 + 2 + 3 + (1 if self.world > 1 else 0) + 3
         stats = self.ranking.host_statistics(st, self.n_total, want_auc=False)          # D2H of NB-length arrays
         return self.ranking.aggregate(stats, self.n_total, want_auc=False), st
 

@@ -34,6 +34,8 @@ SIGNATURES = {
     "frx_topk_merge": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
     "frx_label_stats": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "frx_rank_from_topk": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "frx_missing_thresholds": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    "frx_pack_rank_stats": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "frx_group_positives": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "frx_auc_rows": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "frx_triplet_workspace_bytes": (c_sz, [c_i32, c_i32]),

@@ -249,9 +249,59 @@ __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__
   }
 }
 
+// One [rows, nb] int64 block for the single device->host copy of an evaluation:
+//   0 n_pos   1 first rank inside the top-k list (-1 = none)   2 count before the first positive   3 row 2 is valid
+//   4 hit mask (64 relevance bits)   5 AUC numerator (when given)
+// Row 3: all_valid ? 1 : (first_in_list < 0 && n_pos > 0)  -- the brands whose first positive fell outside the list.
+__global__ void pack_stats_kernel(const int32_t* __restrict__ n_pos, const int32_t* __restrict__ first_in_list,
+                                  const unsigned long long* __restrict__ before_first,
+                                  const unsigned long long* __restrict__ hit_mask,
+                                  const unsigned long long* __restrict__ auc_num, int nb, int all_valid,
+                                  long long* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const int np_ = n_pos[b], fi = first_in_list[b];
+  out[b] = np_;
+  out[(size_t)nb + b] = fi;
+  out[(size_t)2 * nb + b] = (long long)before_first[b];
+  out[(size_t)3 * nb + b] = all_valid ? 1 : ((fi < 0 && np_ > 0) ? 1 : 0);
+  out[(size_t)4 * nb + b] = (long long)hit_mask[b];
+  if (auc_num) out[(size_t)5 * nb + b] = (long long)auc_num[b];
+}
+
+// thr_index[b] = best_index[b] where the first positive is missing from the list, else -1 (the count pass skips it)
+__global__ void missing_threshold_kernel(const int32_t* __restrict__ n_pos, const int32_t* __restrict__ first_in_list,
+                                         const int32_t* __restrict__ best_index, int nb, int32_t* __restrict__ thr_index) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  thr_index[b] = (first_in_list[b] < 0 && n_pos[b] > 0) ? best_index[b] : -1;
+}
+
 }  // namespace frx
 
 extern "C" {
+
+int frx_pack_rank_stats(const int32_t* n_pos, const int32_t* first_in_list, const unsigned long long* before_first,
+                        const unsigned long long* hit_mask, const unsigned long long* auc_num, int nb, int all_valid,
+                        long long* out, void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(n_pos && first_in_list && before_first && hit_mask && out, "frx_pack_rank_stats: NULL pointer");
+  FRX_CHECK_ARG(nb > 0, "frx_pack_rank_stats: bad size");
+  pack_stats_kernel<<<(nb + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n_pos, first_in_list, before_first, hit_mask, auc_num,
+                                                                         nb, all_valid, out);
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
+int frx_missing_thresholds(const int32_t* n_pos, const int32_t* first_in_list, const int32_t* best_index, int nb,
+                           int32_t* thr_index, void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(n_pos && first_in_list && best_index && thr_index, "frx_missing_thresholds: NULL pointer");
+  FRX_CHECK_ARG(nb > 0, "frx_missing_thresholds: bad size");
+  missing_threshold_kernel<<<(nb + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n_pos, first_in_list, best_index, nb, thr_index);
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
 
 int frx_label_stats(const int32_t* labels, const float* pos_score, int64_t n_posts, int nb, int64_t index_base,
                     int32_t* n_pos, float* best_score, int32_t* best_index, void* workspace_nb_u64, void* stream) {

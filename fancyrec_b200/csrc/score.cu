@@ -41,6 +41,7 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = (EPI_WARP0 + NUM_EPI_WARPS) * 32;   // 384
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_MERGE_KEYS = 16384;
+constexpr int MAX_NEED_TILES = 1024;          // COUNT mode tracks per-m-tile skip flags for up to 131072 brands
 constexpr int64_t kSampleMinPosts = 262144;   // below this the warm-up is too short to be worth a sample pass
 // Global per-row candidate histogram (TOPK): bin = (ordered(score) - ordered(sample threshold)) >> HIST_SHIFT, i.e.
 // 64 bins over two octaves of the score above the seeded threshold (32 per octave: the refined threshold sits at most
@@ -84,6 +85,7 @@ struct SmemTail {
   uint32_t tmem_base;
   uint32_t pad;
   uint32_t hist[NUM_EPI_WARPS][256];
+  uint8_t tile_need[MAX_NEED_TILES];   // COUNT: m-tile has at least one row with a threshold (others are skipped)
 };
 constexpr size_t SMEM_BYTES = 1024 /* alignment slack */ + (size_t)STAGES * STAGE_BYTES + sizeof(SmemTail);
 
@@ -253,6 +255,15 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(&tail->tmem_base));
+  if (MODE == MODE_COUNT) {
+    // rows without a threshold (thr_index < 0) are not counted; an m-tile made only of such rows is skipped by all
+    // three roles, so the pass costs only the m-tiles that need it (nothing at all when no first positive is missing)
+    const int nt = P.num_m_tiles < MAX_NEED_TILES ? P.num_m_tiles : MAX_NEED_TILES;
+    for (int i = threadIdx.x; i < nt; i += NUM_THREADS) tail->tile_need[i] = 0;
+    __syncthreads();
+    for (int r = threadIdx.x; r < P.nb && r < MAX_NEED_TILES * BM; r += NUM_THREADS)
+      if (__ldg(P.thr_index + r) >= 0) tail->tile_need[r / BM] = 1;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -267,6 +278,7 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int ks = item % P.k_splits, mi = item / P.k_splits;
         const int m_tile = mi % P.num_m_tiles, split = mi / P.num_m_tiles;
+        if (MODE == MODE_COUNT && m_tile < MAX_NEED_TILES && !tail->tile_need[m_tile]) continue;
         const int kb0 = P.num_k_blocks * ks / P.k_splits, kb1 = P.num_k_blocks * (ks + 1) / P.k_splits;
         const int64_t t0 = P.num_n_tiles * split / P.splits, t1 = P.num_n_tiles * (split + 1) / P.splits;
         for (int64_t t = t0; t < t1; ++t) {
@@ -289,6 +301,10 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       int as = 0; uint32_t aphase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int ks = item % P.k_splits, split = (item / P.k_splits) / P.num_m_tiles;
+        if (MODE == MODE_COUNT) {
+          const int m_tile = (item / P.k_splits) % P.num_m_tiles;
+          if (m_tile < MAX_NEED_TILES && !tail->tile_need[m_tile]) continue;
+        }
         const int kb0 = P.num_k_blocks * ks / P.k_splits, kb1 = P.num_k_blocks * (ks + 1) / P.k_splits;
         const int64_t t0 = P.num_n_tiles * split / P.splits, t1 = P.num_n_tiles * (split + 1) / P.splits;
         for (int64_t t = t0; t < t1; ++t) {
@@ -335,6 +351,7 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int ks = item % P.k_splits, mi = item / P.k_splits;
       const int m_tile = mi % P.num_m_tiles, split = mi / P.num_m_tiles;
+      if (MODE == MODE_COUNT && m_tile < MAX_NEED_TILES && !tail->tile_need[m_tile]) continue;
       const int64_t t0 = P.num_n_tiles * split / P.splits, t1 = P.num_n_tiles * (split + 1) / P.splits;
       const int row = m_tile * BM + row_in_tile;
       const bool row_ok = row < P.nb;

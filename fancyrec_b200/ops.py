@@ -261,6 +261,38 @@ def rank_from_topk(topk_index, labels, index_base=0):
     return hit_mask, first_rank
 
 
+def missing_thresholds(n_pos, first_in_list, best_index):
+    """thr_index for score_count: best_index where the first positive fell outside the top-k list, else -1."""
+    lib = _lib.load()
+    _req(n_pos, torch.int32, "n_pos", 1)
+    _req(first_in_list, torch.int32, "first_in_list", 1)
+    _req(best_index, torch.int32, "best_index", 1)
+    out = torch.empty_like(best_index)
+    with torch.cuda.device(n_pos.device):
+        rc = lib.frx_missing_thresholds(_ptr(n_pos), _ptr(first_in_list), _ptr(best_index), n_pos.numel(), _ptr(out),
+                                        _stream(n_pos))
+    _lib.check(rc, "frx_missing_thresholds")
+    return out
+
+
+def pack_rank_stats(n_pos, first_in_list, before_first, hit_mask, auc_num=None, all_valid=False):
+    """-> int64 [5 | 6, NB]: n_pos, first rank in list, count before first positive, its validity, hit mask (, AUC num)."""
+    lib = _lib.load()
+    _req(n_pos, torch.int32, "n_pos", 1)
+    _req(first_in_list, torch.int32, "first_in_list", 1)
+    _req(before_first, torch.int64, "before_first", 1)
+    _req(hit_mask, torch.int64, "hit_mask", 1)
+    if auc_num is not None:
+        _req(auc_num, torch.int64, "auc_num", 1)
+    nb = n_pos.numel()
+    out = torch.empty((6 if auc_num is not None else 5, nb), dtype=torch.int64, device=n_pos.device)
+    with torch.cuda.device(n_pos.device):
+        rc = lib.frx_pack_rank_stats(_ptr(n_pos), _ptr(first_in_list), _ptr(before_first), _ptr(hit_mask), _ptr(auc_num),
+                                     nb, int(bool(all_valid)), _ptr(out), _stream(n_pos))
+    _lib.check(rc, "frx_pack_rank_stats")
+    return out
+
+
 def group_positives(labels, pos_score, n_pos):
     lib = _lib.load()
     _req(labels, torch.int32, "labels", 1)

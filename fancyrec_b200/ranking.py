@@ -77,27 +77,21 @@ def device_rank_statistics(brand_bf16, post_bf16, labels_i32, d, k=MIN_TOPK, wan
             ops.auc_rows(tile, r0, labels_i32, seg_ptr, pos_sorted, best_score, best_index, auc_num, before_first,
                          index_base)
         out["auc_num"] = auc_num
-        out["before_first_valid"] = torch.ones(nb, dtype=torch.bool, device=dev)
     else:
-        missing = (first_in_list < 0) & (n_pos > 0)
-        if bool(missing.any().item()):
-            thr_index = torch.where(missing, best_index, torch.full_like(best_index, -1))
-            ops.score_count(brand_bf16, post_bf16, best_score, thr_index, d=d, index_base=index_base,
-                            out=before_first)
-        out["before_first_valid"] = missing
+        # enqueued unconditionally: frx_score_count skips every 128-brand tile without a missing first positive
+        thr_index = ops.missing_thresholds(n_pos, first_in_list, best_index)
+        ops.score_count(brand_bf16, post_bf16, best_score, thr_index, d=d, index_base=index_base, out=before_first)
     out["before_first"] = before_first
     return out
 
 
-def host_statistics(dev_stats, n_posts, want_auc=True):
+def host_statistics(dev_stats, n_posts, want_auc=True, kernels=ops):
     """Device statistics -> the integer per-brand arrays the metrics are functions of (NumPy, host).
-    Everything is packed into one int64 [rows, NB] tensor so that the device->host read is ONE copy."""
-    rows = [dev_stats["n_pos"].to(torch.int64), dev_stats["first_in_list"].to(torch.int64),
-            dev_stats["before_first"].to(torch.int64), dev_stats["before_first_valid"].to(torch.int64),
-            dev_stats["hit_mask"].to(torch.int64)]
-    if want_auc:
-        rows.append(dev_stats["auc_num"].to(torch.int64))
-    packed = torch.stack(rows).cpu().numpy()
+    Everything is packed by one kernel into one int64 [rows, NB] tensor so that the device->host read is ONE copy
+    (`kernels`: provider of the device steps, as in sharded.py)."""
+    packed = kernels.pack_rank_stats(dev_stats["n_pos"], dev_stats["first_in_list"], dev_stats["before_first"],
+                                 dev_stats["hit_mask"], dev_stats["auc_num"] if want_auc else None,
+                                 all_valid=want_auc).cpu().numpy()
     n_pos, first_in_list, before, valid, mask = packed[0], packed[1], packed[2], packed[3] != 0, packed[4]
     first_rank = np.where(valid, before, first_in_list)
     first_rank = np.where(n_pos > 0, first_rank, -1)

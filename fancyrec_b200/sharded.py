@@ -102,13 +102,12 @@ def sharded_rank_statistics(brand_op, post_op_local, labels_local, d, k, n_posts
     best_s, best_i = global_best(best_s_l, best_i_l, group)
     labels_all = gather_labels(labels_local, n_posts_total, group)
     hit_mask, first_in_list = kernels.rank_from_topk(top_i, labels_all, 0)
-    missing = (first_in_list < 0) & (n_pos > 0)
+    # Count pass (rank of a first positive that fell outside the list), enqueued unconditionally: the kernel skips every
+    # 128-brand tile without a missing row, so it returns at once in the common case -- no host round trip to decide.
     before = torch.zeros(nb, dtype=torch.int64, device=post_op_local.device)
-    need_count = bool(missing.any().item())        # same decision on every rank (inputs are global)
-    if need_count:
-        thr_index = torch.where(missing, best_i, torch.full_like(best_i, -1))
-        kernels.score_count(brand_op, post_op_local, best_s, thr_index, d=d, index_base=lo, out=before)
-        all_sum(before, group)
+    thr_index = kernels.missing_thresholds(n_pos, first_in_list, best_i)
+    kernels.score_count(brand_op, post_op_local, best_s, thr_index, d=d, index_base=lo, out=before)
+    all_sum(before, group)
     return dict(topk_scores=top_s, topk_index=top_i, n_pos=n_pos, best_score=best_s, best_index=best_i,
                 hit_mask=hit_mask, first_in_list=first_in_list, before_first=before,
-                before_first_valid=missing, workspace=res.get("workspace"), count_pass=need_count)
+                workspace=res.get("workspace"))

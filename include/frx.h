@@ -126,7 +126,8 @@ int frx_score_dense(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* po
  * the stated order: #{ j : S[b,j] > thr_score[b]  or  (S[b,j] == thr_score[b] and index_base + j <
  * thr_index[b]) }.  With the threshold set to a brand's best positive this IS rank_of_first_pos
  * (evaluator.py:116) without materialising S.  count_out [nb] int64 is ACCUMULATED into (caller
- * zeroes it; shards add up).  Rows with thr_index[b] < 0 are skipped. */
+ * zeroes it; shards add up).  Rows with thr_index[b] < 0 are skipped, and so is every 128-brand tile made only of such
+ * rows (the launch returns immediately when no row has a threshold). */
 int frx_score_count(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* post_bf16, int64_t ld_b,
                     int nb, int64_t n_posts, int d, int64_t index_base,
                     const float* thr_score, const int32_t* thr_index,
@@ -189,6 +190,18 @@ int frx_label_stats(const int32_t* labels, const float* pos_score, int64_t n_pos
  * labels are indexed with (topk_index - index_base); entries outside [0, n_posts) count as misses. */
 int frx_rank_from_topk(const int32_t* topk_index, int nb, int k, const int32_t* labels, int64_t n_posts,
                        int64_t index_base, unsigned long long* hit_mask, int32_t* first_rank, void* stream);
+
+/* frx_missing_thresholds: thr_index[b] = best_index[b] for the brands whose first positive is NOT in the top-k list
+ * (first_rank[b] < 0 and n_pos[b] > 0), else -1.  With thr_score = best_score this is the input of frx_score_count, which
+ * skips every 128-brand tile that has no such row -- so the count pass can be enqueued unconditionally (no host
+ * round trip to decide): it costs nothing when every first positive was found in the list (evaluator.py:116).
+ * frx_pack_rank_stats: the per-brand integers an evaluation returns to the host as ONE [5|6, nb] int64 block
+ * (n_pos, first rank in list, count before first positive, validity of that count, hit mask, AUC numerator if given). */
+int frx_missing_thresholds(const int32_t* n_pos, const int32_t* first_in_list, const int32_t* best_index, int nb,
+                           int32_t* thr_index, void* stream);
+int frx_pack_rank_stats(const int32_t* n_pos, const int32_t* first_in_list, const unsigned long long* before_first,
+                        const unsigned long long* hit_mask, const unsigned long long* auc_num, int nb, int all_valid,
+                        long long* out, void* stream);
 
 /* frx_auc_rows: exact AUC numerators from dense score rows (evaluator.py:111-113):
  *   auc_num[row0 + r] += sum over positives e of brand (row0+r) of #{negatives el : e > el}

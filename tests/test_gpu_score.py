@@ -263,6 +263,42 @@ def test_count_pass_matches_oracle():
         assert got[r] == int(np.where(order == tj[r])[0][0])
 
 
+@pytest.mark.parametrize("need", ["none", "one_tile", "scattered"])
+def test_count_pass_skips_tiles_without_thresholds(need):
+    """frx_score_count skips every 128-brand tile whose rows all have thr_index < 0 (and returns at once when no row
+    has a threshold): counts of the rows that DO have one are unchanged, all others stay zero."""
+    from fancyrec_b200 import ops
+    rs = np.random.RandomState(33)
+    nb, npost, d = 400, 9000, 64                  # 4 m-tiles
+    brand = rs.standard_normal((nb, d)).astype(np.float32)
+    posts = rs.standard_normal((npost, d)).astype(np.float32)
+    a, b = operand(brand), operand(posts)
+    dense = ops.score_dense(a, b, d=d).cpu().numpy()
+    tj = rs.randint(0, npost, nb)
+    tidx = np.full(nb, -1, np.int32)
+    rows = {"none": [], "one_tile": [130, 200, 255], "scattered": [0, 127, 128, 399]}[need]
+    tidx[rows] = tj[rows]
+    out = ops.score_count(a, b, to_dev(dense[np.arange(nb), tj].copy()), to_dev(tidx), d=d).cpu().numpy()
+    for r in range(nb):
+        want = int(np.where(oref.order_desc(dense[r]) == tj[r])[0][0]) if r in rows else 0
+        assert out[r] == want
+
+
+def test_missing_thresholds_and_packed_stats():
+    from fancyrec_b200 import ops
+    n_pos = to_dev(np.array([3, 0, 5, 1], np.int32))
+    first = to_dev(np.array([-1, -1, 7, -1], np.int32))
+    best = to_dev(np.array([11, -1, 22, 33], np.int32))
+    assert ops.missing_thresholds(n_pos, first, best).cpu().tolist() == [11, -1, -1, 33]
+    before = to_dev(np.array([100, 0, 0, 2 ** 40], np.int64))
+    mask = to_dev(np.array([0, 0, 1 << 7, -1], np.int64))
+    packed = ops.pack_rank_stats(n_pos, first, before, mask).cpu().numpy()
+    assert packed.tolist() == [[3, 0, 5, 1], [-1, -1, 7, -1], [100, 0, 0, 2 ** 40], [1, 0, 0, 1], [0, 0, 128, -1]]
+    auc = to_dev(np.array([9, 8, 7, 6], np.int64))
+    packed = ops.pack_rank_stats(n_pos, first, before, mask, auc, all_valid=True).cpu().numpy()
+    assert packed[3].tolist() == [1, 1, 1, 1] and packed[5].tolist() == [9, 8, 7, 6]
+
+
 def test_topk_merge_matches_oracle():
     from fancyrec_b200 import ops
     rs = np.random.RandomState(31)

@@ -79,6 +79,18 @@ class OracleKernels:
         return out
 
 
+    def missing_thresholds(self, n_pos, first_in_list, best_index):
+        missing = (first_in_list < 0) & (n_pos > 0)
+        return torch.where(missing, best_index, torch.full_like(best_index, -1))
+
+    def pack_rank_stats(self, n_pos, first_in_list, before_first, hit_mask, auc_num=None, all_valid=False):
+        valid = torch.ones_like(before_first) if all_valid else ((first_in_list < 0) & (n_pos > 0)).to(torch.int64)
+        rows = [n_pos.to(torch.int64), first_in_list.to(torch.int64), before_first, valid, hit_mask]
+        if auc_num is not None:
+            rows.append(auc_num)
+        return torch.stack(rows)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -96,7 +108,7 @@ def _worker(rank, world, port, k, out_dir):
     st = sharded.sharded_rank_statistics(torch.zeros(nb, 8), torch.zeros(hi - lo, 8),
                                          torch.from_numpy(lab[lo:hi].astype(np.int32)), 8, k, n_posts,
                                          kernels=OracleKernels(scores))
-    stats = ranking.host_statistics(st, n_posts, want_auc=False)
+    stats = ranking.host_statistics(st, n_posts, want_auc=False, kernels=OracleKernels(scores))
     res = ranking.aggregate(stats, n_posts, want_auc=False)
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), first_rank=stats["first_rank"], n_pos=stats["n_pos"],
              hits=stats["hits"], topk=st["topk_index"].numpy(), res=np.array([float(x) for x in res]))

@@ -26,10 +26,12 @@ def step(trace):
     n_pos, bs, bi = ops.label_stats(labels, res["pos_score"], nb, 0)
     hit, first = ops.rank_from_topk(res["index"], labels, 0)
     mark("stats")
-    missing = (first < 0) & (n_pos > 0)
-    t0 = time.perf_counter(); need = bool(missing.any().item()); t1 = time.perf_counter()
-    mark("sync1")
-    st = dict(n_pos=n_pos, first_in_list=first, before_first=torch.zeros(nb, dtype=torch.int64, device=dev), before_first_valid=missing, hit_mask=hit)
+    before = torch.zeros(nb, dtype=torch.int64, device=dev)
+    thr_index = ops.missing_thresholds(n_pos, first, bi)
+    ops.score_count(brand_op, post_op, bs, thr_index, d=3072, out=before)
+    mark("count")
+    t0 = t1 = time.perf_counter()
+    st = dict(n_pos=n_pos, first_in_list=first, before_first=before, hit_mask=hit)
     t2 = time.perf_counter(); hs = ranking.host_statistics(st, n, False); t3 = time.perf_counter()
     out = ranking.aggregate(hs, n, False); t4 = time.perf_counter()
     mark("end")
