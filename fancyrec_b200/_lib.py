@@ -31,9 +31,11 @@ SIGNATURES = {
     "frx_score_count_tf32": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "frx_softmax_pool": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "frx_split_tf32x3": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp]),
+    "frx_topk_merge_strided": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp, c_i32, c_vp]),
     "frx_topk_merge": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
     "frx_label_stats": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "frx_rank_from_topk": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "frx_reduce_shard_stats": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "frx_missing_thresholds": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "frx_pack_rank_stats": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "frx_group_positives": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),

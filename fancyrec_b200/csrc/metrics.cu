@@ -277,9 +277,49 @@ __global__ void missing_threshold_kernel(const int32_t* __restrict__ n_pos, cons
   thr_index[b] = (first_in_list[b] < 0 && n_pos[b] > 0) ? best_index[b] : -1;
 }
 
+// Multi-GPU exchange, after the all-gather of every shard's (n_pos, best positive): n_pos = sum over shards, best
+// positive = the largest (score, ~index) key over the shards that have one.  Shard g's arrays start `stride` 32-bit
+// words after shard g-1's (they live inside the packed all-gather buffer).
+__global__ void reduce_shard_stats_kernel(const int32_t* __restrict__ n_pos_g, const float* __restrict__ best_s_g,
+                                          const int32_t* __restrict__ best_i_g, int g, int nb, int64_t stride,
+                                          int32_t* __restrict__ n_pos, float* __restrict__ best_score,
+                                          int32_t* __restrict__ best_index) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  int total = 0;
+  unsigned long long best = 0ull;
+  for (int r = 0; r < g; ++r) {
+    total += n_pos_g[(int64_t)r * stride + b];
+    const int32_t idx = best_i_g[(int64_t)r * stride + b];
+    if (idx >= 0) {
+      const unsigned long long key = make_key(best_s_g[(int64_t)r * stride + b], (uint32_t)idx);
+      best = key > best ? key : best;
+    }
+  }
+  n_pos[b] = total;
+  if (best != 0ull) {
+    best_score[b] = key_score(best);
+    best_index[b] = (int32_t)key_index(best);
+  } else {
+    best_score[b] = -INFINITY;
+    best_index[b] = -1;
+  }
+}
+
 }  // namespace frx
 
 extern "C" {
+
+int frx_reduce_shard_stats(const int32_t* n_pos_g, const float* best_score_g, const int32_t* best_index_g, int g, int nb,
+                           int64_t stride_words, int32_t* n_pos, float* best_score, int32_t* best_index, void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(n_pos_g && best_score_g && best_index_g && n_pos && best_score && best_index, "frx_reduce_shard_stats: NULL pointer");
+  FRX_CHECK_ARG(g >= 1 && nb >= 1 && stride_words >= nb, "frx_reduce_shard_stats: bad sizes");
+  reduce_shard_stats_kernel<<<(nb + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n_pos_g, best_score_g, best_index_g, g, nb,
+                                                                                 stride_words, n_pos, best_score, best_index);
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
 
 int frx_pack_rank_stats(const int32_t* n_pos, const int32_t* first_in_list, const unsigned long long* before_first,
                         const unsigned long long* hit_mask, const unsigned long long* auc_num, int nb, int all_valid,

@@ -786,8 +786,8 @@ __global__ void seed_threshold_kernel(const float* __restrict__ topk_scores, int
 
 // Merge g lists [g, nb, k_in] of (score, index) into [nb, k_out] (multi-GPU exchange step).
 __global__ void __launch_bounds__(256) merge_lists_kernel(const float* __restrict__ in_s, const int32_t* __restrict__ in_i,
-                                                          int g, int nb, int k_in, float* __restrict__ out_s,
-                                                          int32_t* __restrict__ out_i, int k_out) {
+                                                          int g, int nb, int k_in, int64_t shard_stride,
+                                                          float* __restrict__ out_s, int32_t* __restrict__ out_i, int k_out) {
   extern __shared__ unsigned long long skeys[];
   const int b = blockIdx.x;
   const int total = g * k_in;
@@ -796,7 +796,7 @@ __global__ void __launch_bounds__(256) merge_lists_kernel(const float* __restric
     unsigned long long key = 0ull;
     if (i < total) {
       const int gi = i / k_in, ki = i % k_in;
-      const size_t src = ((size_t)gi * nb + b) * k_in + ki;
+      const size_t src = (size_t)gi * shard_stride + (size_t)b * k_in + ki;
       const int32_t idx = in_i[src];
       if (idx >= 0) key = make_key(in_s[src], (uint32_t)idx);
     }
@@ -1252,20 +1252,27 @@ int frx_probe_read(float* host_ms_out, int max) {
   return n;
 }
 
-int frx_topk_merge(const float* in_scores, const int32_t* in_index, int g, int nb, int k_in, float* out_scores,
-                   int32_t* out_index, int k_out, void* stream) {
+int frx_topk_merge_strided(const float* in_scores, const int32_t* in_index, int g, int nb, int k_in, int64_t shard_stride,
+                           float* out_scores, int32_t* out_index, int k_out, void* stream) {
   using namespace frx;
   FRX_CHECK_ARG(in_scores && in_index && out_scores && out_index, "frx_topk_merge: NULL pointer");
   FRX_CHECK_ARG(g >= 1 && nb >= 1 && k_in >= 1 && k_out >= 1, "frx_topk_merge: bad sizes");
+  FRX_CHECK_ARG(shard_stride >= (int64_t)nb * k_in, "frx_topk_merge: shard stride %lld below nb * k_in", (long long)shard_stride);
   FRX_CHECK_ARG((long)g * k_in <= MAX_MERGE_KEYS, "frx_topk_merge: g*k_in = %ld exceeds %d", (long)g * k_in, MAX_MERGE_KEYS);
   int np2 = 2;
   while (np2 < g * k_in) np2 <<= 1;
   const size_t msmem = (size_t)np2 * sizeof(unsigned long long);
   if (msmem > 32 * 1024)
     FRX_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-  merge_lists_kernel<<<nb, 256, msmem, (cudaStream_t)stream>>>(in_scores, in_index, g, nb, k_in, out_scores, out_index, k_out);
+  merge_lists_kernel<<<nb, 256, msmem, (cudaStream_t)stream>>>(in_scores, in_index, g, nb, k_in, shard_stride, out_scores,
+                                                               out_index, k_out);
   FRX_LAUNCH_CHECK();
   return FRX_OK;
+}
+
+int frx_topk_merge(const float* in_scores, const int32_t* in_index, int g, int nb, int k_in, float* out_scores,
+                   int32_t* out_index, int k_out, void* stream) {
+  return frx_topk_merge_strided(in_scores, in_index, g, nb, k_in, (int64_t)nb * k_in, out_scores, out_index, k_out, stream);
 }
 
 }  // extern "C"

@@ -229,6 +229,37 @@ def topk_merge(scores, index, k_out):
     return out_s, out_i
 
 
+def merge_gathered(gathered, nb, k_in, k_out):
+    """Multi-GPU exchange, device side.  `gathered` int32 [G, W]: rank r's row is the packed block
+    [scores nb*k_in (fp32 bits) | index nb*k_in | n_pos nb | best_score nb (fp32 bits) | best_index nb] it contributed to
+    the all-gather.  Returns (top scores [nb, k_out], top index, n_pos [nb], best_score [nb], best_index [nb]) of the
+    whole job: the lists are merged and the label statistics combined in place out of that buffer (two kernels)."""
+    lib = _lib.load()
+    if not (isinstance(gathered, torch.Tensor) and gathered.is_cuda and gathered.dtype == torch.int32 and
+            gathered.dim() == 2 and gathered.stride(1) == 1):
+        raise _lib.FrxError("gathered must be a 2-D int32 CUDA tensor with unit column stride")
+    g, head = gathered.shape
+    w = gathered.stride(0) if g > 1 else head          # rows may be longer than the head (labels ride behind it)
+    if head != 2 * nb * k_in + 3 * nb:
+        raise ValueError("packed row has %d words, expected %d" % (head, 2 * nb * k_in + 3 * nb))
+    dev = gathered.device
+    out_s = torch.empty((nb, k_out), dtype=torch.float32, device=dev)
+    out_i = torch.empty((nb, k_out), dtype=torch.int32, device=dev)
+    n_pos = torch.empty(nb, dtype=torch.int32, device=dev)
+    best_s = torch.empty(nb, dtype=torch.float32, device=dev)
+    best_i = torch.empty(nb, dtype=torch.int32, device=dev)
+    base = gathered.data_ptr()
+    o_idx, o_np = 4 * nb * k_in, 8 * nb * k_in
+    with torch.cuda.device(dev):
+        rc = lib.frx_topk_merge_strided(base, base + o_idx, g, nb, k_in, w, _ptr(out_s), _ptr(out_i), k_out,
+                                        _stream(gathered))
+        _lib.check(rc, "frx_topk_merge_strided")
+        rc = lib.frx_reduce_shard_stats(base + o_np, base + o_np + 4 * nb, base + o_np + 8 * nb, g, nb, w, _ptr(n_pos),
+                                        _ptr(best_s), _ptr(best_i), _stream(gathered))
+        _lib.check(rc, "frx_reduce_shard_stats")
+    return out_s, out_i, n_pos, best_s, best_i
+
+
 # ---------------------------------------------------------------------------------------------
 def label_stats(labels, pos_score, nb, index_base=0):
     lib = _lib.load()

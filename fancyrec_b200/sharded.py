@@ -4,8 +4,9 @@ Posts are independent columns of the score matrix: rank r owns the contiguous ra
 [NP*r/G, NP*(r+1)/G) (global index = offset + local, so the (score desc, index asc) comparator is
 shard-invariant) and the small brand operand is replicated.  Each rank runs the fused score + top-k
 kernel on its shard; the only data-path exchange is ONE all-gather of the per-brand candidate lists
-([NB, k] x (fp32 score, int32 global index)) followed by a merge with the same comparator, plus
-NB-length reductions of the integer statistics.  One process per GPU, torch.distributed (NCCL over
+([NB, k] x (fp32 score, int32 global index), with the NB-length label statistics and the labels (4 B / post)
+riding in the same buffer) followed by a merge with the same comparator, plus one NB-length all-reduce of the
+count-pass result.  One process per GPU, torch.distributed (NCCL over
 NVLink on the box, gloo in the CPU tests).
 
 `kernels` is the provider of the device steps (default: fancyrec_b200.ops, i.e. libfrx_b200.so); the
@@ -35,45 +36,6 @@ def _all_gather_stack(t, group=None):
     return flat.view((world,) + tuple(t.shape))
 
 
-def gather_lists(scores, index, group=None):
-    """[NB, k] per rank -> ([G, NB, k] scores, [G, NB, k] index), identical on every rank."""
-    world, _ = _world(group)
-    if world == 1:
-        return scores.unsqueeze(0), index.unsqueeze(0)
-    return _all_gather_stack(scores, group), _all_gather_stack(index, group)
-
-
-def gather_labels(labels_local, n_posts, group=None):
-    """Concatenate the label shards in rank order -> [n_posts] on every rank."""
-    world, _ = _world(group)
-    if world == 1:
-        return labels_local
-    sizes = [shard_bounds(n_posts, world, r)[1] - shard_bounds(n_posts, world, r)[0] for r in range(world)]
-    width = max(sizes)                       # ragged shards are padded to a common width for the collective
-    padded = torch.zeros(width, dtype=labels_local.dtype, device=labels_local.device)
-    padded[:labels_local.numel()] = labels_local
-    stacked = _all_gather_stack(padded, group)
-    return torch.cat([stacked[r, :sizes[r]] for r in range(world)])
-
-
-def global_best(best_score, best_index, group=None):
-    """Per brand, the best positive over all shards under (score desc, index asc); index < 0 = none."""
-    world, _ = _world(group)
-    if world == 1:
-        return best_score, best_index
-    gs = _all_gather_stack(best_score, group)
-    gi = _all_gather_stack(best_index, group)
-    valid = gi >= 0
-    s = torch.where(valid, gs, torch.full_like(gs, float("-inf")))
-    top = s.max(dim=0).values
-    big = torch.iinfo(gi.dtype).max
-    cand = torch.where(valid & (s == top.unsqueeze(0)), gi, torch.full_like(gi, big))
-    idx = cand.min(dim=0).values
-    none = ~valid.any(dim=0)
-    idx = torch.where(none, torch.full_like(idx, -1), idx)
-    return top, idx
-
-
 def all_sum(t, group=None):
     world, _ = _world(group)
     if world > 1:
@@ -93,14 +55,21 @@ def sharded_rank_statistics(brand_op, post_op_local, labels_local, d, k, n_posts
     res = kernels.score_topk(brand_op, post_op_local, k, d=d, labels=labels_local, index_base=lo,
                              workspace=workspace)
     n_pos_l, best_s_l, best_i_l = kernels.label_stats(labels_local, res["pos_score"], nb, lo)
-    gs, gi = gather_lists(res["scores"], res["index"], group)
     if world > 1:
-        top_s, top_i = kernels.topk_merge(gs, gi, k)
+        # ONE all-gather: every rank contributes [scores | index | n_pos | best score | best index | labels] as 32-bit
+        # words; the lists are merged and the label statistics combined in place out of the gathered buffer.
+        sizes = [shard_bounds(n_posts_total, world, r)[1] - shard_bounds(n_posts_total, world, r)[0] for r in range(world)]
+        width = max(sizes)                           # ragged shards are padded to a common width for the collective
+        pad = labels_local.new_zeros(width - labels_local.numel())
+        packed = torch.cat([res["scores"].reshape(-1).view(torch.int32), res["index"].reshape(-1), n_pos_l,
+                            best_s_l.view(torch.int32), best_i_l, labels_local, pad])
+        gathered = _all_gather_stack(packed, group)
+        head = 2 * nb * k + 3 * nb
+        top_s, top_i, n_pos, best_s, best_i = kernels.merge_gathered(gathered[:, :head], nb, k, k)
+        labels_all = torch.cat([gathered[r, head:head + sizes[r]] for r in range(world)])
     else:
-        top_s, top_i = res["scores"], res["index"]
-    n_pos = all_sum(n_pos_l.clone(), group)
-    best_s, best_i = global_best(best_s_l, best_i_l, group)
-    labels_all = gather_labels(labels_local, n_posts_total, group)
+        top_s, top_i, n_pos, best_s, best_i = res["scores"], res["index"], n_pos_l, best_s_l, best_i_l
+        labels_all = labels_local
     hit_mask, first_in_list = kernels.rank_from_topk(top_i, labels_all, 0)
     # Count pass (rank of a first positive that fell outside the list), enqueued unconditionally: the kernel skips every
     # 128-brand tile without a missing row, so it returns at once in the common case -- no host round trip to decide.

@@ -170,6 +170,10 @@ int frx_score_count_tf32(const float* brand_f32, int64_t ld_a, const float* post
  * padding.  Requires g * k_in <= 16384. */
 int frx_topk_merge(const float* in_scores, const int32_t* in_index, int g, int nb, int k_in,
                    float* out_scores, int32_t* out_index, int k_out, void* stream);
+/* Same, reading shard r's [nb, k_in] lists at in_scores + r * shard_stride / in_index + r * shard_stride (elements):
+ * the lists are merged in place out of the packed all-gather buffer of the multi-GPU exchange. */
+int frx_topk_merge_strided(const float* in_scores, const int32_t* in_index, int g, int nb, int k_in,
+                           int64_t shard_stride, float* out_scores, int32_t* out_index, int k_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * A6-A9  rank statistics (integers; the float64 metric values are functions of these).
@@ -190,6 +194,13 @@ int frx_label_stats(const int32_t* labels, const float* pos_score, int64_t n_pos
  * labels are indexed with (topk_index - index_base); entries outside [0, n_posts) count as misses. */
 int frx_rank_from_topk(const int32_t* topk_index, int nb, int k, const int32_t* labels, int64_t n_posts,
                        int64_t index_base, unsigned long long* hit_mask, int32_t* first_rank, void* stream);
+
+/* frx_reduce_shard_stats (multi-GPU): combine the per-shard label statistics after their all-gather.
+ * Shard r's n_pos / best_score / best_index arrays ([nb] each) start r * stride_words 32-bit words after shard 0's
+ * (so they can be read in place from one packed all-gather buffer).  n_pos = sum over shards; the best positive is
+ * the maximum over shards under (score desc, index asc); (-inf, -1) when no shard has one. */
+int frx_reduce_shard_stats(const int32_t* n_pos_g, const float* best_score_g, const int32_t* best_index_g, int g, int nb,
+                           int64_t stride_words, int32_t* n_pos, float* best_score, int32_t* best_index, void* stream);
 
 /* frx_missing_thresholds: thr_index[b] = best_index[b] for the brands whose first positive is NOT in the top-k list
  * (first_rank[b] < 0 and n_pos[b] > 0), else -1.  With thr_score = best_score this is the input of frx_score_count, which

@@ -79,6 +79,23 @@ class OracleKernels:
         return out
 
 
+    def merge_gathered(self, gathered, nb, k_in, k_out):
+        g = gathered.shape[0]
+        rows = [gathered[r].contiguous() for r in range(g)]
+        o = nb * k_in
+        sc = torch.stack([r[:o].view(torch.float32).reshape(nb, k_in) for r in rows])
+        ix = torch.stack([r[o:2 * o].reshape(nb, k_in) for r in rows])
+        top_s, top_i = self.topk_merge(sc, ix, k_out)
+        n_pos = torch.stack([r[2 * o:2 * o + nb] for r in rows]).sum(0).to(torch.int32)
+        gs = torch.stack([r[2 * o + nb:2 * o + 2 * nb].view(torch.float32) for r in rows])
+        gi = torch.stack([r[2 * o + 2 * nb:2 * o + 3 * nb] for r in rows])
+        valid = gi >= 0                      # best positive over the shards under (score desc, index asc)
+        s = torch.where(valid, gs, torch.full_like(gs, float("-inf")))
+        top = s.max(dim=0).values
+        cand = torch.where(valid & (s == top.unsqueeze(0)), gi, torch.full_like(gi, torch.iinfo(gi.dtype).max))
+        idx = torch.where(~valid.any(dim=0), torch.full_like(cand[0], -1), cand.min(dim=0).values)
+        return top_s, top_i, n_pos, top, idx
+
     def missing_thresholds(self, n_pos, first_in_list, best_index):
         missing = (first_in_list < 0) & (n_pos > 0)
         return torch.where(missing, best_index, torch.full_like(best_index, -1))
