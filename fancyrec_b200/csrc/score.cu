@@ -29,13 +29,24 @@
 namespace frx {
 using namespace sm100;
 
-constexpr int BM = 128, BN = 256, STAGES = 4;
+constexpr int BM = 128, BN = 256;
 // one k-block = one 128-byte swizzle row per operand row: 64 bf16 or 32 tf32 (fp32 storage); 4 MMAs per k-block
 // (K = 16 bf16 / 8 tf32 = 32 bytes each), so stage bytes and the per-MMA descriptor advance are the same in both modes
 constexpr int BK_BYTES = 128, MMAS_PER_KBLOCK = 4;
 constexpr int A_STAGE_BYTES = BM * BK_BYTES;   // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK_BYTES;   // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int MAX_STAGES = 6;
+// Shared-memory ring.  Single CTA: 4 stages of {A 128 x 64, B 256 x 64} = 48 KB.  CTA pair (cta_group::2, one 256 x 256
+// MMA tile per pair): each CTA stages its own 128 rows of A and HALF of the B tile, 32 KB per stage -> 6 stages in the
+// same 192 KB, and a third less L2 -> shared-memory operand traffic per flop.
+template <bool PAIR>
+struct Ring {
+  static constexpr int STAGES = PAIR ? 6 : 4;
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;
+  static constexpr int B_BYTES = B_ROWS * BK_BYTES;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_BYTES;
+};
+constexpr int RING_BYTES = Ring<false>::STAGES * Ring<false>::STAGE_BYTES;   // 192 KB in both layouts
+static_assert(RING_BYTES == Ring<true>::STAGES * Ring<true>::STAGE_BYTES, "both ring layouts use the same shared memory");
 constexpr int EPI_WARP0 = 4;                 // warps 4..11: lane quarter = warp % 4, column half = (warp-4)/4
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = (EPI_WARP0 + NUM_EPI_WARPS) * 32;   // 384
@@ -81,13 +92,13 @@ struct ScoreParams {
 };
 
 struct SmemTail {
-  uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+  uint64_t full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
   uint32_t hist[NUM_EPI_WARPS][256];
   uint8_t tile_need[MAX_NEED_TILES];   // COUNT: m-tile has at least one row with a threshold (others are skipped)
 };
-constexpr size_t SMEM_BYTES = 1024 /* alignment slack */ + (size_t)STAGES * STAGE_BYTES + sizeof(SmemTail);
+constexpr size_t SMEM_BYTES = 1024 /* alignment slack */ + (size_t)RING_BYTES + sizeof(SmemTail);
 
 // ---------------------------------------------------------------------------------------------
 // Warp-cooperative MSB-first radix select over one row's candidate keys.
@@ -234,27 +245,39 @@ __device__ __forceinline__ int hist_edge(const uint32_t* hrow, uint32_t k) {
   return -1;
 }
 
-template <int MODE, bool TF32>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-             const ScoreParams P) {
+template <int MODE, bool TF32, bool PAIR>
+__device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ScoreParams& P) {
+  using R = Ring<PAIR>;
+  constexpr int STAGES = R::STAGES;
+  constexpr int B_STAGE = R::B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;            // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
-  SmemTail* tail = reinterpret_cast<SmemTail*>(smem + (size_t)STAGES * STAGE_BYTES);
+  SmemTail* tail = reinterpret_cast<SmemTail*>(smem + (size_t)RING_BYTES);
   const uint32_t smem_a = base, smem_b = base + STAGES * A_STAGE_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int BK = TF32 ? 32 : 64;                      // operand elements per k-block
+  // CTA pair: cluster rank 0 = leader (issues the MMAs); the pair shares one scheduling slot and one 256-row m-unit
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const int slot = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nslots = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_units = PAIR ? (P.num_m_tiles >> 1) : P.num_m_tiles;   // the host pads num_m_tiles to even for pairs
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&tail->full[s]), 1); mbar_init(smem_u32(&tail->empty[s]), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tail->tmem_full[s]), 1); mbar_init(smem_u32(&tail->tmem_empty[s]), NUM_EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tail->tmem_full[s]), 1);
+      mbar_init(smem_u32(&tail->tmem_empty[s]), NUM_EPI_WARPS * (PAIR ? 2 : 1));   // the leader hears both CTAs' epilogues
+    }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(&tail->tmem_base));
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_pair<TMEM_COLS>(smem_u32(&tail->tmem_base));
+    else tmem_alloc<TMEM_COLS>(smem_u32(&tail->tmem_base));
+  }
   if (MODE == MODE_COUNT) {
     // rows without a threshold (thr_index < 0) are not counted; an m-tile made only of such rows is skipped by all
     // three roles, so the pass costs only the m-tiles that need it (nothing at all when no first positive is missing)
@@ -265,46 +288,69 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       if (__ldg(P.thr_index + r) >= 0) tail->tile_need[r / BM] = 1;
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();      // the peer's barriers are initialised before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
 
-  const int n_items = P.num_m_tiles * P.splits * P.k_splits;      // item = (split * num_m_tiles + m_tile) * k_splits + ks
+  // item = (split * m_units + m_unit) * k_splits + ks ; a unit is one 128-row m-tile, or the pair's two m-tiles
+  const int n_items = m_units * P.splits * P.k_splits;
+  auto unit_skipped = [&](int mu) -> bool {                 // COUNT only; both CTAs of a pair take the same decision
+    if (MODE != MODE_COUNT) return false;
+    const int t0_ = PAIR ? 2 * mu : mu, t1_ = PAIR ? 2 * mu + 1 : mu;
+    if (t1_ >= MAX_NEED_TILES) return false;
+    return !(tail->tile_need[t0_] | tail->tile_need[t1_]);
+  };
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = slot; item < n_items; item += nslots) {
         const int ks = item % P.k_splits, mi = item / P.k_splits;
-        const int m_tile = mi % P.num_m_tiles, split = mi / P.num_m_tiles;
-        if (MODE == MODE_COUNT && m_tile < MAX_NEED_TILES && !tail->tile_need[m_tile]) continue;
+        const int mu = mi % m_units, split = mi / m_units;
+        if (unit_skipped(mu)) continue;
+        const int m_tile = PAIR ? 2 * mu + (int)crank : mu;
         const int kb0 = P.num_k_blocks * ks / P.k_splits, kb1 = P.num_k_blocks * (ks + 1) / P.k_splits;
         const int64_t t0 = P.num_n_tiles * split / P.splits, t1 = P.num_n_tiles * (split + 1) / P.splits;
         for (int64_t t = t0; t < t1; ++t) {
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(smem_u32(&tail->empty[stage]), phase ^ 1);
             const uint32_t fb = smem_u32(&tail->full[stage]);
-            mbar_arrive_expect_tx(fb, STAGE_BYTES);
-            tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, fb, kb * BK, m_tile * BM);
-            tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, fb, kb * BK, (int32_t)(t * BN));
+            if (PAIR) {
+              // both CTAs' bytes are counted on the LEADER's barrier (the only thread that waits for operands is its
+              // MMA issuer); this CTA brings its 128 rows of A and its half of the B tile
+              if (crank == 0) mbar_arrive_expect_tx(fb, 2 * R::STAGE_BYTES);
+              const uint32_t lfb = mapa_shared(fb, 0);
+              tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tmap_a, lfb, kb * BK, m_tile * BM);
+              tma_load_2d_pair(smem_b + stage * B_STAGE, &tmap_b, lfb, kb * BK, (int32_t)(t * BN + crank * (BN / 2)));
+            } else {
+              mbar_arrive_expect_tx(fb, R::STAGE_BYTES);
+              tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, fb, kb * BK, m_tile * BM);
+              tma_load_2d(smem_b + stage * B_STAGE, &tmap_b, fb, kb * BK, (int32_t)(t * BN));
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+        }
+      }
+      if (PAIR) {
+        // drain: every multicast "slot free" arrival aimed at this CTA has landed before it may exit
+        for (int i = 0; i < STAGES; ++i) {
+          mbar_wait(smem_u32(&tail->empty[stage]), phase ^ 1);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(BM, BN) : make_idesc_bf16(BM, BN);
+    if (lane == 0 && crank == 0) {                         // of a pair only the leader issues; its MMAs span both SMs
+      constexpr int MMA_M = PAIR ? 2 * BM : BM;
+      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(MMA_M, BN) : make_idesc_bf16(MMA_M, BN);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int ks = item % P.k_splits, split = (item / P.k_splits) / P.num_m_tiles;
-        if (MODE == MODE_COUNT) {
-          const int m_tile = (item / P.k_splits) % P.num_m_tiles;
-          if (m_tile < MAX_NEED_TILES && !tail->tile_need[m_tile]) continue;
-        }
+      for (int item = slot; item < n_items; item += nslots) {
+        const int ks = item % P.k_splits, mi = item / P.k_splits;
+        const int mu = mi % m_units, split = mi / m_units;
+        if (unit_skipped(mu)) continue;
         const int kb0 = P.num_k_blocks * ks / P.k_splits, kb1 = P.num_k_blocks * (ks + 1) / P.k_splits;
         const int64_t t0 = P.num_n_tiles * split / P.splits, t1 = P.num_n_tiles * (split + 1) / P.splits;
         for (int64_t t = t0; t < t1; ++t) {
@@ -318,16 +364,23 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             mbar_wait(smem_u32(&tail->full[stage]), phase);
             tc_fence_after();
             const uint64_t da = make_sw128_kmajor_desc(smem_a + stage * A_STAGE_BYTES);
-            const uint64_t db = make_sw128_kmajor_desc(smem_b + stage * B_STAGE_BYTES);
+            const uint64_t db = make_sw128_kmajor_desc(smem_b + stage * B_STAGE);
 #pragma unroll
             for (int k = 0; k < MMAS_PER_KBLOCK; ++k) {
               // advance 16 bf16 / 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
-              if (TF32) umma_tf32_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0));
-              else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0));
+              const uint32_t acc = (kb > kb0 || k > 0);
+              if (PAIR) {
+                if (TF32) umma_tf32_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, acc);
+                else umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, acc);
+              } else {
+                if (TF32) umma_tf32_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, acc);
+                else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, acc);
+              }
             }
-            umma_commit(smem_u32(&tail->empty[stage]));        // frees the smem slot when the MMAs retire
+            // frees the smem slot (in both CTAs of a pair) when the MMAs retire
+            if (PAIR) umma_commit_pair(smem_u32(&tail->empty[stage]), 3); else umma_commit(smem_u32(&tail->empty[stage]));
             if (kb == kb1 - 1) {
-              umma_commit(smem_u32(&tail->tmem_full[as]));
+              if (PAIR) umma_commit_pair(smem_u32(&tail->tmem_full[as]), 3); else umma_commit(smem_u32(&tail->tmem_full[as]));
 #ifdef FRX_TRACE
               if (P.trace && blockIdx.x == 0 && (t - t0) < 256) P.trace[(t - t0) * 4 + 1] = clock64();
 #endif
@@ -348,10 +401,11 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     constexpr int CHUNKS = BN / 2 / 32;              // 4 chunks of 32 columns per warp per tile
     uint32_t* hist = tail->hist[ew];
     int as = 0; uint32_t aphase = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = slot; item < n_items; item += nslots) {
       const int ks = item % P.k_splits, mi = item / P.k_splits;
-      const int m_tile = mi % P.num_m_tiles, split = mi / P.num_m_tiles;
-      if (MODE == MODE_COUNT && m_tile < MAX_NEED_TILES && !tail->tile_need[m_tile]) continue;
+      const int mu = mi % m_units, split = mi / m_units;
+      if (unit_skipped(mu)) continue;
+      const int m_tile = PAIR ? 2 * mu + (int)crank : mu;     // this CTA's 128 accumulator lanes = these brand rows
       const int64_t t0 = P.num_n_tiles * split / P.splits, t1 = P.num_n_tiles * (split + 1) / P.splits;
       const int row = m_tile * BM + row_in_tile;
       const bool row_ok = row < P.nb;
@@ -359,7 +413,8 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       // per-row state
       float thr = row_ok ? -INFINITY : INFINITY;     // TOPK: append threshold
       int cnt = 0;                                   // TOPK: candidates buffered
-      const size_t part = ((size_t)item * 2 + h) * BM;            // candidate lists of this (item, half)
+      // candidate lists of this (split, m-tile, column half)
+      const size_t part = ((((size_t)split * P.num_m_tiles + m_tile) * P.k_splits + ks) * 2 + h) * BM;
       unsigned long long* rowbuf = nullptr;
       float ts = 0.f; int32_t ti = -1; unsigned long long ccount = 0;
       if (MODE == MODE_TOPK) rowbuf = P.part_keys + (part + row_in_tile) * P.cap;
@@ -523,7 +578,10 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #ifdef FRX_TRACE
         if (P.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && (t - t0) < 256) P.trace[(t - t0) * 4 + 3] = clock64();
 #endif
-        if (lane == 0) mbar_arrive(smem_u32(&tail->tmem_empty[as]));
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&tail->tmem_empty[as]), 0));   // the leader's barrier
+          else mbar_arrive(smem_u32(&tail->tmem_empty[as]));
+        }
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
 
@@ -549,11 +607,26 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 
   // =========================== teardown ===========================
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();      // neither CTA of a pair exits while the other may still signal it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
+}
+
+template <int MODE, bool TF32>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+             const __grid_constant__ ScoreParams P) {
+  score_body<MODE, TF32, false>(tmap_a, tmap_b, P);
+}
+
+// The same kernel on CTA pairs: clusters of two CTAs (the two SMs of a TPC), tcgen05 cta_group::2.
+template <int MODE, bool TF32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+score_kernel_pair(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ ScoreParams P) {
+  score_body<MODE, TF32, true>(tmap_a, tmap_b, P);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -853,16 +926,29 @@ static int make_operand_map(CUtensorMap* map, const void* ptr, int64_t rows, int
   return FRX_OK;
 }
 
+// CTA pairs (cta_group::2) are the default; FRX_PAIR=0 selects the single-CTA kernel (A/B measurements, fallback).
+static bool use_pair() {
+  static const int v = getenv("FRX_PAIR") ? atoi(getenv("FRX_PAIR")) : 1;
+  return v != 0 && num_sms() % 2 == 0;
+}
+
 struct Plan {
-  int num_m_tiles, splits, cap, keep_limit, grid;
+  bool pair;          // one scheduling unit = a CTA pair working on 256 brand rows
+  int num_m_tiles;    // 128-row m-tiles (padded to an even count for pairs: candidate lists are addressed by m-tile)
+  int m_units, slots; // schedulable m-units (m-tiles or pairs of them) and concurrently resident units
+  int splits, cap, keep_limit, grid;
   int64_t num_n_tiles;
   size_t keys_bytes, cnt_bytes, thr_bytes;
 };
 
 static Plan make_plan(int nb, int64_t n_posts, int k, int mode) {
   Plan p{};
-  const int sms = num_sms();
-  p.num_m_tiles = (nb + BM - 1) / BM;
+  p.pair = use_pair();
+  const int real_m_tiles = (nb + BM - 1) / BM;
+  p.num_m_tiles = p.pair ? (real_m_tiles + 1) / 2 * 2 : real_m_tiles;
+  p.m_units = p.pair ? p.num_m_tiles / 2 : p.num_m_tiles;
+  p.slots = p.pair ? num_sms() / 2 : num_sms();
+  const int sms = p.slots;
   p.num_n_tiles = (n_posts + BN - 1) / BN;
   int64_t smax = p.num_n_tiles;
   if (smax > 1024) smax = 1024;
@@ -870,15 +956,16 @@ static Plan make_plan(int nb, int64_t n_posts, int k, int mode) {
   // pick the split count that fills whole waves of `sms` CTAs; prefer fewer, longer items
   int best = 1; double best_eff = -1.0;
   for (int s = 1; s <= (int)smax; ++s) {
-    const long items = (long)p.num_m_tiles * s;
+    const long items = (long)p.m_units * s;
     const long waves = (items + sms - 1) / sms;
     double eff = (double)items / (double)(waves * sms);
     if (waves > 8 && s > 1) break;               // long enough; more splits only add merge work
     if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
   }
   p.splits = best;
-  const long items = (long)p.num_m_tiles * p.splits;
-  p.grid = (int)(items < sms ? items : sms);
+  const long units = (long)p.m_units * p.splits;
+  p.grid = (int)(units < sms ? units : sms) * (p.pair ? 2 : 1);
+  const long items = (long)p.num_m_tiles * p.splits;             // candidate lists exist per (split, m-tile)
   int cap = 1024;
   while (cap < 4 * k) cap <<= 1;
   p.cap = cap;
@@ -951,7 +1038,7 @@ static int launch_score(const void* a, int64_t ld_a, const void* b, int64_t ld_b
   CUtensorMap ma, mb;
   int rc = make_operand_map(&ma, a, nb, d, ld_a, BM, TF32);
   if (rc) return rc;
-  rc = make_operand_map(&mb, b, n_posts, d, ld_b, BN, TF32);
+  rc = make_operand_map(&mb, b, n_posts, d, ld_b, plan.pair ? BN / 2 : BN, TF32);   // a pair's CTAs load half a B tile each
   if (rc) return rc;
   P.nb = nb;
   P.n_posts = n_posts;
@@ -964,7 +1051,10 @@ static int launch_score(const void* a, int64_t ld_a, const void* b, int64_t ld_b
 #ifdef FRX_TRACE
   P.trace = (MODE == MODE_TOPK && allow_probe) ? g_trace : nullptr;
 #endif
-  FRX_CUDA(cudaFuncSetAttribute(score_kernel<MODE, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  if (plan.pair)
+    FRX_CUDA(cudaFuncSetAttribute(score_kernel_pair<MODE, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  else
+    FRX_CUDA(cudaFuncSetAttribute(score_kernel<MODE, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   const bool probe = allow_probe && MODE == MODE_TOPK && g_probe.on && g_probe.n < 4096;   // main fused launches only
   const int slot = g_probe.n;
   if (probe) {
@@ -975,9 +1065,10 @@ static int launch_score(const void* a, int64_t ld_a, const void* b, int64_t ld_b
     }
     FRX_CUDA(cudaEventRecord(g_probe.beg[slot], st));
   }
-  long total_items = (long)plan.num_m_tiles * plan.splits * P.k_splits;
-  const int grid = (int)(total_items < num_sms() ? total_items : num_sms());
-  score_kernel<MODE, TF32><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
+  const long total_units = (long)plan.m_units * plan.splits * P.k_splits;
+  const int grid = (int)(total_units < plan.slots ? total_units : plan.slots) * (plan.pair ? 2 : 1);
+  if (plan.pair) score_kernel_pair<MODE, TF32><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);   // clusters of 2 CTAs
+  else score_kernel<MODE, TF32><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
   FRX_LAUNCH_CHECK();
   if (probe) {
     FRX_CUDA(cudaEventRecord(g_probe.end[slot], st));
@@ -1024,7 +1115,7 @@ static int score_dense_impl(const void* a, int64_t ld_a, const void* b, int64_t 
   P.ld_dense = ld_dense;
   // Small outputs (the B x B loss tile) cover only a few tiles: split K over the idle SMs and reduce afterwards.
   const int sms = num_sms();
-  const long tile_units = (long)plan.num_m_tiles * plan.num_n_tiles;
+  const long tile_units = (long)plan.m_units * plan.num_n_tiles * (plan.pair ? 2 : 1);   // SMs busy without a K split
   const int nkb = (d + (TF32 ? 32 : 64) - 1) / (TF32 ? 32 : 64);
   int k_splits = 1;
   if (ksplit_ws != nullptr && tile_units * 2 <= sms) {
