@@ -926,9 +926,15 @@ static int make_operand_map(CUtensorMap* map, const void* ptr, int64_t rows, int
   return FRX_OK;
 }
 
-// CTA pairs (cta_group::2) are the default; FRX_PAIR=0 selects the single-CTA kernel (A/B measurements, fallback).
+// Two variants of the same kernel: one CTA per SM (default), or CTA pairs (cta_group::2, one 256 x 256 MMA tile per
+// pair).  Measured on B200 under its 1 kW cap: the pair variant needs ~6 % fewer cycles per tile at
+// D = 3072 (a third less L2 -> shared-memory operand traffic, deeper ring) but the cross-SM operand reads cost power, the
+// SM clock settles ~7 % lower and wall-clock time is equal or slightly worse -- so it is opt-in: FRX_PAIR=1 or
+// frx_set_cta_pairs(1).
+static int g_pair_mode = -1;                      // -1: take the FRX_PAIR environment variable (default 0)
 static bool use_pair() {
-  static const int v = getenv("FRX_PAIR") ? atoi(getenv("FRX_PAIR")) : 1;
+  static const int env = getenv("FRX_PAIR") ? atoi(getenv("FRX_PAIR")) : 0;
+  const int v = g_pair_mode >= 0 ? g_pair_mode : env;
   return v != 0 && num_sms() % 2 == 0;
 }
 
@@ -1325,6 +1331,12 @@ int frx_score_count_tf32(const float* brand_f32, int64_t ld_a, const float* post
 #ifdef FRX_TRACE
 int frx_debug_set_trace(long long* device_buf) { frx::g_trace = device_buf; return 0; }
 #endif
+
+int frx_set_cta_pairs(int on) {
+  const int prev = frx::use_pair() ? 1 : 0;
+  frx::g_pair_mode = on < 0 ? -1 : (on != 0 ? 1 : 0);
+  return prev;
+}
 
 int frx_probe_enable(int on) {
   frx::g_probe.on = on != 0;

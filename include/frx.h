@@ -279,6 +279,12 @@ int frx_lab_fwd_bwd(const float* brand, int b, int d, float* loss, float* d_bran
  * and clears the log.  Off by default; at most 4096 launches are logged.
  */
 int frx_probe_enable(int on);
+
+/* Kernel variant of every frx_score_* entry point: 0 = one CTA per SM (default), 1 = CTA pairs (tcgen05 cta_group::2:
+ * the two SMs of a TPC share one 256 x 256 MMA tile, each staging its 128 brand rows and half of the post tile),
+ * -1 = back to the FRX_PAIR environment variable.  Results are identical bit for bit (same accumulation order per
+ * output element).  Returns the previous setting.  Process-wide; not for concurrent use with running launches. */
+int frx_set_cta_pairs(int on);
 int frx_probe_read(float* host_ms_out, int max);
 
 #ifdef __cplusplus

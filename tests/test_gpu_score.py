@@ -198,6 +198,71 @@ def test_adversarial_orders_large_np(kind, k):
     assert np.array_equal(res["pos_score"].cpu().numpy(), dense[lab, np.arange(npost)])
 
 
+@pytest.fixture
+def cta_pairs():
+    """Run the body on the CTA-pair (tcgen05 cta_group::2) variant of the score kernel."""
+    from fancyrec_b200 import _lib
+    lib = _lib.load()
+    prev = lib.frx_set_cta_pairs(1)
+    yield
+    lib.frx_set_cta_pairs(prev)
+
+
+@pytest.mark.parametrize("nb,npost,d,k", [
+    (5, 257, 48, 10), (130, 3000, 200, 100), (300, 70001, 256, 100), (64, 5000, 3072, 1000), (129, 513, 72, 1),
+    (1000, 20000, 128, 100), (385, 300000, 64, 64),      # odd m-tile counts leave the second CTA of a pair without rows
+])
+def test_cta_pair_variant_bit_identical(cta_pairs, nb, npost, d, k):
+    """The cta_group::2 variant must give bit for bit what the single-CTA kernel gives: dense tile, fused top-k
+    (incl. the sample-seeded / histogram-refined path at 300 k posts), positives' scores and the count pass."""
+    from fancyrec_b200 import _lib, ops
+    lib = _lib.load()
+    rs = np.random.RandomState(nb + npost + 1)
+    brand = rs.standard_normal((nb, d)).astype(np.float32)
+    posts = rs.standard_normal((npost, d)).astype(np.float32)
+    lab = synth.labels(5, npost, nb)
+    res, dense, a, b = _dense_and_topk(brand, posts, k, labels=lab, index_base=9)
+    want = oref.topk_indices(dense, k)
+    kk = min(k, npost)
+    assert np.array_equal(res["index"].cpu().numpy()[:, :kk], want + 9)
+    assert np.array_equal(res["scores"].cpu().numpy()[:, :kk], np.take_along_axis(dense, want, 1))
+    assert np.array_equal(res["pos_score"].cpu().numpy(), dense[lab, np.arange(npost)])
+    tj = rs.randint(0, npost, nb)
+    tidx = (tj + 9).astype(np.int32)
+    tidx[::3] = -1
+    cnt = ops.score_count(a, b, to_dev(dense[np.arange(nb), tj].copy()), to_dev(tidx), d=d, index_base=9).cpu().numpy()
+    lib.frx_set_cta_pairs(0)                              # single-CTA kernel on the same operands
+    dense1 = ops.score_dense(a, b, d=d).cpu().numpy()
+    res1 = ops.score_topk(a, b, k, d=d, labels=to_dev(lab.astype(np.int32)), index_base=9)
+    cnt1 = ops.score_count(a, b, to_dev(dense[np.arange(nb), tj].copy()), to_dev(tidx), d=d, index_base=9).cpu().numpy()
+    lib.frx_set_cta_pairs(1)
+    assert np.array_equal(dense, dense1)
+    assert torch.equal(res["index"], res1["index"]) and torch.equal(res["scores"], res1["scores"])
+    assert np.array_equal(cnt, cnt1)
+
+
+def test_cta_pair_variant_tf32_and_loss_tiles(cta_pairs):
+    """tf32 operands and the K-split dense path (the B x B loss tile) on CTA pairs."""
+    from fancyrec_b200 import loss as floss, ops, ranking
+    rs = np.random.RandomState(2)
+    nb, npost, d = 70, 3000, 256
+    brand = rs.standard_normal((nb, d)).astype(np.float32)
+    posts = rs.standard_normal((npost, d)).astype(np.float32)
+    a = ranking.to_operand(to_dev(brand), precision="tf32x3", side=ranking.BRAND_SIDE)
+    b = ranking.to_operand(to_dev(posts), precision="tf32x3", side=ranking.POST_SIDE)
+    dense = ops.score_dense(a, b, d=3 * d).cpu().numpy()
+    assert np.abs(dense - oref.cal_sim(brand, posts)).max() <= 1e-5
+    ids = to_dev(rs.randint(0, 20, 512).astype(np.int64))
+    be, pe = to_dev(rs.standard_normal((512, 1024)).astype(np.float32)), to_dev(rs.standard_normal((512, 1024)).astype(np.float32))
+    crit = floss.TripletLoss(margin=0.2)
+    pair_val = crit(ids, be, pe).item()
+    from fancyrec_b200 import _lib
+    _lib.load().frx_set_cta_pairs(0)
+    single_val = crit(ids, be, pe).item()
+    _lib.load().frx_set_cta_pairs(1)
+    assert pair_val == single_val
+
+
 def test_heavy_ties_and_index_base():
     """Quantised scores (few distinct values) -> the tie-break carries the whole ranking."""
     rs = np.random.RandomState(3)
