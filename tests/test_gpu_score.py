@@ -263,6 +263,47 @@ def test_cta_pair_variant_tf32_and_loss_tiles(cta_pairs):
     assert pair_val == single_val
 
 
+@pytest.mark.parametrize("pairs", [0, 1])
+def test_random_shape_sweep(pairs):
+    """40 seeded random problems (ragged sizes around the tile boundaries, k around n_posts, quantised scores with
+    heavy ties every third case): exact top-k, positives' scores and count pass against the oracle on our tile, on
+    both kernel variants."""
+    from fancyrec_b200 import _lib, ops
+    lib = _lib.load()
+    prev = lib.frx_set_cta_pairs(pairs)
+    try:
+        rs = np.random.RandomState(1234 + pairs)
+        for case in range(40):
+            nb = int(rs.choice([1, 2, 31, 127, 128, 129, 200, 255, 256, 257, 300]))
+            npost = int(rs.choice([1, 3, 63, 255, 256, 257, 511, 513, 1000, 4099]))
+            d = int(rs.choice([4, 8, 60, 64, 68, 128, 200]))
+            k = int(rs.choice([1, 2, 10, 64, 100, 333, 1024]))
+            if case % 3 == 0:
+                brand = rs.randint(-2, 3, size=(nb, d)).astype(np.float32)
+                posts = rs.randint(-2, 3, size=(npost, d)).astype(np.float32)
+                brand[np.abs(brand).sum(1) == 0, 0] = 1.0
+                posts[np.abs(posts).sum(1) == 0, 0] = 1.0
+            else:
+                brand = rs.standard_normal((nb, d)).astype(np.float32)
+                posts = rs.standard_normal((npost, d)).astype(np.float32)
+            lab = rs.randint(0, nb, npost).astype(np.int64)
+            base = int(rs.choice([0, 1, 77777]))
+            res, dense, a, b = _dense_and_topk(brand, posts, k, labels=lab, index_base=base)
+            want = oref.topk_indices(dense, k)
+            kk = min(k, npost)
+            msg = "case %d: nb=%d npost=%d d=%d k=%d" % (case, nb, npost, d, k)
+            assert np.array_equal(res["index"].cpu().numpy()[:, :kk], want + base), msg
+            assert np.array_equal(res["scores"].cpu().numpy()[:, :kk], np.take_along_axis(dense, want, 1)), msg
+            assert np.array_equal(res["pos_score"].cpu().numpy(), dense[lab, np.arange(npost)]), msg
+            tj = rs.randint(0, npost, nb)
+            cnt = ops.score_count(a, b, to_dev(dense[np.arange(nb), tj].copy()), to_dev((tj + base).astype(np.int32)),
+                                  d=d, index_base=base).cpu().numpy()
+            r = int(rs.randint(0, nb))
+            assert cnt[r] == int(np.where(oref.order_desc(dense[r]) == tj[r])[0][0]), msg
+    finally:
+        lib.frx_set_cta_pairs(prev)
+
+
 def test_heavy_ties_and_index_base():
     """Quantised scores (few distinct values) -> the tie-break carries the whole ranking."""
     rs = np.random.RandomState(3)
