@@ -89,6 +89,7 @@ struct ScoreParams {
   const int32_t* thr_index;
   unsigned long long* count_out;
   long long* trace;                // FRX_TRACE builds only: per-tile clock64 stamps of CTA 0 (4 per tile)
+  long long* cta_trace;            // FRX_TRACE builds only: per CTA {smid, globaltimer at start, at tile 50, at the end}
 };
 
 struct SmemTail {
@@ -401,6 +402,15 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
     constexpr int CHUNKS = BN / 2 / 32;              // 4 chunks of 32 columns per warp per tile
     uint32_t* hist = tail->hist[ew];
     int as = 0; uint32_t aphase = 0;
+#ifdef FRX_TRACE
+    if (P.cta_trace && ew == 0 && lane == 0) {
+      uint32_t smid; unsigned long long gt;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      P.cta_trace[blockIdx.x * 4 + 0] = smid;
+      P.cta_trace[blockIdx.x * 4 + 1] = (long long)gt;
+    }
+#endif
     for (int item = slot; item < n_items; item += nslots) {
       const int ks = item % P.k_splits, mi = item / P.k_splits;
       const int mu = mi % m_units, split = mi / m_units;
@@ -456,6 +466,13 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
         }
         mbar_wait(smem_u32(&tail->tmem_full[as]), aphase);
         tc_fence_after();
+#ifdef FRX_TRACE
+        if (P.cta_trace && ew == 0 && lane == 0 && item == slot && (t - t0) == 50) {
+          unsigned long long gt;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+          P.cta_trace[blockIdx.x * 4 + 2] = (long long)gt;
+        }
+#endif
 #ifdef FRX_TRACE
         if (P.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && (t - t0) < 256) P.trace[(t - t0) * 4 + 2] = clock64();
 #endif
@@ -606,6 +623,13 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
   }
 
   // =========================== teardown ===========================
+#ifdef FRX_TRACE
+  if (P.cta_trace && threadIdx.x == EPI_WARP0 * 32) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    P.cta_trace[blockIdx.x * 4 + 3] = (long long)gt;
+  }
+#endif
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();      // neither CTA of a pair exits while the other may still signal it
   if (warp == 2) {
@@ -985,6 +1009,7 @@ static Plan make_plan(int nb, int64_t n_posts, int k, int mode) {
 // ---- measurement hook: CUDA events around each score_kernel launch --------------------------
 #ifdef FRX_TRACE
 static long long* g_trace = nullptr;     // debug builds only (tools/gpu_trace_pipeline.py)
+static long long* g_cta_trace = nullptr; // debug builds only (tools/gpu_trace_ctas.py)
 #endif
 
 struct Probe {
@@ -1056,6 +1081,7 @@ static int launch_score(const void* a, int64_t ld_a, const void* b, int64_t ld_b
   if (P.k_splits < 1) P.k_splits = 1;
 #ifdef FRX_TRACE
   P.trace = (MODE == MODE_TOPK && allow_probe) ? g_trace : nullptr;
+  P.cta_trace = (MODE == MODE_TOPK && allow_probe) ? g_cta_trace : nullptr;
 #endif
   if (plan.pair)
     FRX_CUDA(cudaFuncSetAttribute(score_kernel_pair<MODE, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -1330,6 +1356,7 @@ int frx_score_count_tf32(const float* brand_f32, int64_t ld_a, const float* post
 
 #ifdef FRX_TRACE
 int frx_debug_set_trace(long long* device_buf) { frx::g_trace = device_buf; return 0; }
+int frx_debug_set_cta_trace(long long* device_buf) { frx::g_cta_trace = device_buf; return 0; }
 #endif
 
 int frx_set_cta_pairs(int on) {
