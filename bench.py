@@ -358,7 +358,7 @@ def run_e2e(ev, w, e, labels, visual, text, args, dev, world):
     ms = max_over_ranks(beg.elapsed_time(end), dev, world) / steps
     pairs = float(ev.nb) * float(n_local) * world
     h2d = n_local * (dv + dt) * 4 + n_local * 4
-    d2h = ev.nb * (4 + 4 + 8 + 8 + 1)
+    d2h = ev.nb * 5 * 8                      # the packed int64 [5, NB] statistics block
     return {"value": pairs / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "api": "ops.brand_embed + ingest.finalize_from_host (pinned host -> device, chunked, overlapped) + "
