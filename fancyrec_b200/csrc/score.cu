@@ -717,11 +717,9 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long
     return __ldcg(list_ptr(lo) + (g - offs[lo]));
   };
   if (staged) {
-    for (int s = 0; s < lists; ++s) {
-      const int n = offs[s + 1] - offs[s];
-      const unsigned long long* src = list_ptr(s);
-      for (int i = threadIdx.x; i < n; i += blockDim.x) skeys[offs[s] + i] = src[i];
-    }
+    // flattened gather: every candidate of every list is one independent load (a per-list loop would serialise
+    // dozens of L2 round trips over lists that hold a handful of entries each)
+    for (int g = threadIdx.x; g < total; g += blockDim.x) skeys[g] = fetch(g);
     __syncthreads();
   } else {
     // Too many candidates for shared memory: most of them were appended under an early, loose threshold.  Keep only
