@@ -405,6 +405,32 @@ def test_missing_thresholds_and_packed_stats():
     assert packed[3].tolist() == [1, 1, 1, 1] and packed[5].tolist() == [9, 8, 7, 6]
 
 
+@pytest.mark.parametrize("nb,npost", [(300, 200000), (2048, 70000), (3000, 200000), (50, 999)])
+def test_label_stats_both_paths(nb, npost):
+    """n_pos and the best positive per brand (ties -> smaller index), shared-memory-privatised kernel (nb <= 2048,
+    many posts) and the plain one; labels outside [0, nb) are ignored; brands without positives give (-inf, -1)."""
+    from fancyrec_b200 import ops
+    rs = np.random.RandomState(nb + npost)
+    lab = rs.randint(-2, nb + 3, npost).astype(np.int32)
+    lab[lab == 7] = 8                                           # brand 7 has no positive
+    score = (rs.randint(-20, 21, npost) / 16.0).astype(np.float32)   # heavy ties
+    base = 1000
+    n_pos, bs, bi = ops.label_stats(to_dev(lab), to_dev(score), nb, base)
+    n_pos, bs, bi = n_pos.cpu().numpy(), bs.cpu().numpy(), bi.cpu().numpy()
+    ok = (lab >= 0) & (lab < nb)
+    assert np.array_equal(n_pos, np.bincount(lab[ok], minlength=nb))
+    order = np.lexsort((np.arange(npost), -score))              # score desc, index asc
+    first = {}
+    for j in order:
+        if ok[j] and lab[j] not in first:
+            first[lab[j]] = j
+    for b in range(nb):
+        if b in first:
+            assert bi[b] == first[b] + base and bs[b] == score[first[b]]
+        else:
+            assert bi[b] == -1 and np.isneginf(bs[b])
+
+
 def test_topk_merge_matches_oracle():
     from fancyrec_b200 import ops
     rs = np.random.RandomState(31)
