@@ -155,23 +155,19 @@ class Evaluator:
 
     def step(self, w, e, labels, visual, text):
         ops = self.ops
-        # brand side (FMA-bound, 0.5 ms) on a second stream, concurrent with the HBM-bound post finalisation
-        main = torch.cuda.current_stream(self.dev)
-        side = self.ranking.side_stream(self.dev)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            brand = ops.brand_embed(w, e, nb=self.nb)                                  # 1 kernel
-            brand_op = ops.finalize_posts(brand, final_norm=True)[1]                    # 1
+        # brand side first (two small tensor-core launches), then the HBM-bound post finalisation.  Running the brand side
+        # on a second stream was measured 0.5 ms/step SLOWER: its persistent GEMM cannot share SMs with the finalise blocks.
+        brand = ops.brand_embed(w, e, nb=self.nb)                                      # split x2 + 3xTF32 GEMM
+        brand_op = ops.finalize_posts(brand, final_norm=True)[1]                        # 1
         post_op = ops.finalize_posts(visual, text, visual_norm=True, text_norm=True, final_norm=True)[1]   # 1
-        main.wait_stream(side)
-        brand.record_stream(main); brand_op.record_stream(main)
         st = self.sharded.sharded_rank_statistics(brand_op, post_op, labels, self.d, self.cfg["k"], self.n_total,
                                                   workspace=self.workspace)
         self.workspace = st["workspace"]
-        # brand_embed, 2 x finalize | sample pass: dense score + row k-th select | main: score + merge | label_stats,
-        # decode_best, rank_from_topk (+ merge_lists when sharded, + count pass when a first positive is deep)
-        # ... missing_thresholds, score_count (returns at once unless a first positive is missing), pack_rank_stats
-        self.launches = 3 + 2 + 2 + 3 + (1 if self.world > 1 else 0) + 3
+        # our kernels per step (profiles/r01i_launches.csv): brand_embed = split_rows + split_transpose + 3xTF32 GEMM |
+        # 2 x finalize | sample pass: dense score + row k-th select | main: fused score + merge | label_stats, decode_best,
+        # rank_from_topk | missing_thresholds, score_count (returns at once unless a first positive is missing),
+        # pack_rank_stats | sharded: merge of the gathered lists + reduce_shard_stats
+        self.launches = 3 + 2 + 2 + 2 + 3 + 3 + (2 if self.world > 1 else 0)
         stats = self.ranking.host_statistics(st, self.n_total, want_auc=False)          # D2H of NB-length arrays
         return self.ranking.aggregate(stats, self.n_total, want_auc=False), st
 

@@ -167,18 +167,6 @@ def aggregate(stats, n_posts, want_auc=True):
             np.average(n10), np.average(n50), r1, r5, r10)
 
 
-_SIDE_STREAMS = {}
-
-
-def side_stream(device):
-    """A second stream per device for the small brand-side kernels, which are FMA-bound and overlap with the
-    HBM-bound post finalisation running on the current stream."""
-    key = torch.device(device).index
-    if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
-    return _SIDE_STREAMS[key]
-
-
 def rank_posts(brand_f32, post_f32, labels, k=MIN_TOPK, want_auc=True):
     """Single-GPU convenience: fp32 brand [NB, D] / post [NP, D] embeddings + labels -> (8-tuple, stats)."""
     labels_i32 = labels.to(torch.int32).contiguous()
