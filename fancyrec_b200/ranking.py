@@ -108,8 +108,8 @@ _IDEAL_CACHE = {}
 
 
 def _ideal_table(depth):
-    """ideal DCG for m = 0..depth ones followed by zeros, each computed with the reference's expression
-    (util/ndcg.py:37-42 on sorted(r, reverse=True)); cached, it only depends on `depth`."""
+    """(ideal DCG for m = 0..depth ones followed by zeros, discounts log2(2..depth), their reciprocals), each ideal value
+    computed with the reference's expression (util/ndcg.py:37-42 on sorted(r, reverse=True)); cached per `depth`."""
     tab = _IDEAL_CACHE.get(depth)
     if tab is None:
         disc = np.log2(np.arange(2, depth + 1)) if depth > 1 else None
@@ -118,22 +118,25 @@ def _ideal_table(depth):
             ideal = np.zeros(depth, dtype=np.float64)
             ideal[:m] = 1.0
             tab[m] = ideal[0] + (np.sum(ideal[1:] / disc) if depth > 1 else 0.0)
-        _IDEAL_CACHE[depth] = (tab, disc)
+        inv = 1.0 / disc if depth > 1 else None
+        _IDEAL_CACHE[depth] = (tab, disc, inv)
         tab = _IDEAL_CACHE[depth]
     return tab
 
 
-def _ndcg_rows(hits_f64, n_pos, k, n_posts):
-    """ndcg_at_k (util/ndcg.py:48-78) for every row of a 0/1 `hits` matrix (float64) at once.  Row reductions run
-    over the contiguous last axis, so NumPy applies to each row the same pairwise summation it applies
-    to the reference's 1-D np.sum -- results are bit-identical (tests/test_abi.py checks this)."""
-    depth = min(k, n_posts, hits_f64.shape[1])
-    table, disc = _ideal_table(depth)
+def _ndcg_rows(hits_u8, n_pos, k, n_posts):
+    """ndcg_at_k (util/ndcg.py:48-78) for every row of a 0/1 `hits` matrix at once.  A hit contributes
+    1.0 / log2(i + 1), which is bit for bit the reference's r[i] / log2(i + 1) for r[i] = 1.0 (a miss contributes 0.0),
+    and the row reductions run over the contiguous last axis of a fresh array, so NumPy applies to each row the same
+    pairwise summation it applies to the reference's 1-D np.sum -- results are bit-identical (tests/test_abi.py)."""
+    depth = min(k, n_posts, hits_u8.shape[1])
+    table, disc, inv = _ideal_table(depth)
+    dcg = hits_u8[:, 0].astype(np.float64)
     if depth > 1:
-        dcg = hits_f64[:, 0] + np.sum(np.ascontiguousarray(hits_f64[:, 1:depth] / disc), axis=1)
-    else:
-        dcg = hits_f64[:, 0].copy()
+        dcg = dcg + np.sum(np.multiply(hits_u8[:, 1:depth], inv), axis=1)
     best = table[np.minimum(n_pos, depth)]
+    if best.all():                       # every row has a positive (the caller filters on n_pos > 0): ideal DCG > 0
+        return dcg / best
     out = np.zeros(len(n_pos), dtype=np.float64)
     nz = best != 0
     out[nz] = dcg[nz] / best[nz]
@@ -160,7 +163,9 @@ def aggregate(stats, n_posts, want_auc=True):
         auc = np.average(num / den)
     else:
         auc = np.float64("nan")
-    hits = np.asarray(stats["hits"])[has].astype(np.float64)
+    hits = np.asarray(stats["hits"])
+    if not has.all():
+        hits = hits[has]
     n10 = _ndcg_rows(hits, n_pos[has], 10, n_posts)
     n50 = _ndcg_rows(hits, n_pos[has], 50, n_posts)
     return (np.floor(np.median(first)), np.floor(np.mean(first)), auc,
