@@ -63,26 +63,36 @@ def device_rank_statistics(brand_bf16, post_bf16, labels_i32, d, k=MIN_TOPK, wan
                pos_score=res["pos_score"])
     before_first = torch.zeros(nb, dtype=torch.int64, device=dev)
     if want_auc:
-        auc_num = torch.zeros(nb, dtype=torch.int64, device=dev)
         seg_ptr, pos_sorted = ops.group_positives(labels_i32, res["pos_score"], n_pos)
-        n_posts = post_bf16.shape[0]
-        rows = max(1, min(nb, DENSE_BUDGET_BYTES // (4 * n_posts)))
-        if rows >= 128:
-            rows = rows // 128 * 128
-        dense = torch.empty((min(rows, nb), n_posts), dtype=torch.float32, device=dev)
-        for r0 in range(0, nb, rows):
-            r1 = min(nb, r0 + rows)
-            tile = dense[:r1 - r0]
-            ops.score_dense(brand_bf16[r0:r1], post_bf16, d=d, out=tile)
-            ops.auc_rows(tile, r0, labels_i32, seg_ptr, pos_sorted, best_score, best_index, auc_num, before_first,
-                         index_base)
-        out["auc_num"] = auc_num
+        out["auc_num"] = auc_sweep(ops, brand_bf16, post_bf16, d, labels_i32, seg_ptr, pos_sorted, best_score,
+                                   best_index, index_base, before_first)
     else:
         # enqueued unconditionally: frx_score_count skips every 128-brand tile without a missing first positive
         thr_index = ops.missing_thresholds(n_pos, first_in_list, best_index)
         ops.score_count(brand_bf16, post_bf16, best_score, thr_index, d=d, index_base=index_base, out=before_first)
     out["before_first"] = before_first
     return out
+
+
+def auc_sweep(kernels, brand_op, post_op, d, labels_i32, seg_ptr, pos_sorted, best_score, best_index, index_base,
+              before_first):
+    """Exact AUC numerators (evaluator.py:111-113) of the posts in `post_op` against the sorted positives in
+    (seg_ptr, pos_sorted) -- which may be the positives of the WHOLE job when `post_op` is one shard of it -- by
+    sweeping dense score tiles of at most DENSE_BUDGET_BYTES, never the whole matrix.  Also accumulates into
+    `before_first` the number of these posts that precede each brand's best positive.  Returns auc_num [NB] int64."""
+    nb, n_posts = brand_op.shape[0], post_op.shape[0]
+    auc_num = torch.zeros(nb, dtype=torch.int64, device=post_op.device)
+    rows = max(1, min(nb, DENSE_BUDGET_BYTES // (4 * max(n_posts, 1))))
+    if rows >= 128:
+        rows = rows // 128 * 128
+    dense = torch.empty((min(rows, nb), n_posts), dtype=torch.float32, device=post_op.device)
+    for r0 in range(0, nb, rows):
+        r1 = min(nb, r0 + rows)
+        tile = dense[:r1 - r0]
+        kernels.score_dense(brand_op[r0:r1], post_op, d=d, out=tile)
+        kernels.auc_rows(tile, r0, labels_i32, seg_ptr, pos_sorted, best_score, best_index, auc_num, before_first,
+                         index_base)
+    return auc_num
 
 
 def host_statistics(dev_stats, n_posts, want_auc=True, kernels=ops):

@@ -44,9 +44,11 @@ def all_sum(t, group=None):
 
 
 def sharded_rank_statistics(brand_op, post_op_local, labels_local, d, k, n_posts_total, group=None,
-                            kernels=_ops, workspace=None):
+                            kernels=_ops, workspace=None, want_auc=False):
     """Device statistics of the WHOLE job from this rank's shard.  Returns the same dict layout as
-    ranking.device_rank_statistics (want_auc=False flavour), identical on every rank."""
+    ranking.device_rank_statistics, identical on every rank.  want_auc: the positives' scores ride in the exchange
+    block too (4 B / post); every rank then sweeps ITS posts against the job-wide sorted positives of each brand and the
+    exact AUC numerators (and the counts before the first positive) are summed over the ranks."""
     world, rank = _world(group)
     lo, hi = shard_bounds(n_posts_total, world, rank)
     assert post_op_local.shape[0] == hi - lo == labels_local.numel()
@@ -61,22 +63,34 @@ def sharded_rank_statistics(brand_op, post_op_local, labels_local, d, k, n_posts
         sizes = [shard_bounds(n_posts_total, world, r)[1] - shard_bounds(n_posts_total, world, r)[0] for r in range(world)]
         width = max(sizes)                           # ragged shards are padded to a common width for the collective
         pad = labels_local.new_zeros(width - labels_local.numel())
-        packed = torch.cat([res["scores"].reshape(-1).view(torch.int32), res["index"].reshape(-1), n_pos_l,
-                            best_s_l.view(torch.int32), best_i_l, labels_local, pad])
-        gathered = _all_gather_stack(packed, group)
+        parts = [res["scores"].reshape(-1).view(torch.int32), res["index"].reshape(-1), n_pos_l,
+                 best_s_l.view(torch.int32), best_i_l, labels_local, pad]
+        if want_auc:
+            parts += [res["pos_score"].view(torch.int32), pad]
+        gathered = _all_gather_stack(torch.cat(parts), group)
         head = 2 * nb * k + 3 * nb
         top_s, top_i, n_pos, best_s, best_i = kernels.merge_gathered(gathered[:, :head], nb, k, k)
         labels_all = torch.cat([gathered[r, head:head + sizes[r]] for r in range(world)])
+        if want_auc:
+            pos_all = torch.cat([gathered[r, head + width:head + width + sizes[r]] for r in range(world)]).view(torch.float32)
     else:
         top_s, top_i, n_pos, best_s, best_i = res["scores"], res["index"], n_pos_l, best_s_l, best_i_l
         labels_all = labels_local
+        pos_all = res["pos_score"]
     hit_mask, first_in_list = kernels.rank_from_topk(top_i, labels_all, 0)
-    # Count pass (rank of a first positive that fell outside the list), enqueued unconditionally: the kernel skips every
-    # 128-brand tile without a missing row, so it returns at once in the common case -- no host round trip to decide.
     before = torch.zeros(nb, dtype=torch.int64, device=post_op_local.device)
-    thr_index = kernels.missing_thresholds(n_pos, first_in_list, best_i)
-    kernels.score_count(brand_op, post_op_local, best_s, thr_index, d=d, index_base=lo, out=before)
+    out = dict(topk_scores=top_s, topk_index=top_i, n_pos=n_pos, best_score=best_s, best_index=best_i,
+               hit_mask=hit_mask, first_in_list=first_in_list, before_first=before, workspace=res.get("workspace"))
+    if want_auc:
+        from . import ranking as _ranking
+        seg_ptr, pos_sorted = kernels.group_positives(labels_all, pos_all, n_pos)        # job-wide positives per brand
+        auc_num = _ranking.auc_sweep(kernels, brand_op, post_op_local, d, labels_local, seg_ptr, pos_sorted, best_s,
+                                     best_i, lo, before)                                  # this shard's posts
+        out["auc_num"] = all_sum(auc_num, group)
+    else:
+        # Count pass (rank of a first positive that fell outside the list), enqueued unconditionally: the kernel skips
+        # every 128-brand tile without a missing row, so it returns at once in the common case -- no host round trip.
+        thr_index = kernels.missing_thresholds(n_pos, first_in_list, best_i)
+        kernels.score_count(brand_op, post_op_local, best_s, thr_index, d=d, index_base=lo, out=before)
     all_sum(before, group)
-    return dict(topk_scores=top_s, topk_index=top_i, n_pos=n_pos, best_score=best_s, best_index=best_i,
-                hit_mask=hit_mask, first_in_list=first_in_list, before_first=before,
-                workspace=res.get("workspace"))
+    return out

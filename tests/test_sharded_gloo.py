@@ -96,6 +96,30 @@ class OracleKernels:
         idx = torch.where(~valid.any(dim=0), torch.full_like(cand[0], -1), cand.min(dim=0).values)
         return top_s, top_i, n_pos, top, idx
 
+    def group_positives(self, labels, pos_score, n_pos):
+        lab, ps, npos = labels.numpy(), pos_score.numpy(), n_pos.numpy()
+        seg = np.concatenate([[0], np.cumsum(npos)]).astype(np.int64)
+        srt = np.concatenate([np.sort(ps[lab == b]) for b in range(len(npos))] + [np.zeros(0, np.float32)])
+        return torch.from_numpy(seg), torch.from_numpy(srt.astype(np.float32))
+
+    def score_dense(self, brand_op, post_op, d=None, out=None):
+        return out                                   # auc_rows reads the oracle's scores directly
+
+    def auc_rows(self, scores, row0, labels, seg_ptr, pos_sorted, best_score, best_index, auc_num, before_first,
+                 index_base=0):
+        lab, seg, srt = labels.numpy(), seg_ptr.numpy(), pos_sorted.numpy()
+        bs, bi = best_score.numpy(), best_index.numpy()
+        s_loc = self._local(index_base, len(lab))
+        j = np.arange(len(lab)) + index_base
+        for r in range(scores.shape[0]):
+            b = row0 + r
+            pos = srt[seg[b]:seg[b + 1]]
+            if len(pos) == 0:
+                continue
+            neg = s_loc[b][lab != b]
+            auc_num[b] += int((len(pos) - np.searchsorted(pos, neg, side="right")).sum())   # positives > negative
+            before_first[b] += int(((s_loc[b] > bs[b]) | ((s_loc[b] == bs[b]) & (j < bi[b]))).sum())
+
     def missing_thresholds(self, n_pos, first_in_list, best_index):
         missing = (first_in_list < 0) & (n_pos > 0)
         return torch.where(missing, best_index, torch.full_like(best_index, -1))
@@ -114,7 +138,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, k, out_dir):
+def _worker(rank, world, port, k, out_dir, want_auc=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -124,11 +148,12 @@ def _worker(rank, world, port, k, out_dir):
     lo, hi = sharded.shard_bounds(n_posts, world, rank)
     st = sharded.sharded_rank_statistics(torch.zeros(nb, 8), torch.zeros(hi - lo, 8),
                                          torch.from_numpy(lab[lo:hi].astype(np.int32)), 8, k, n_posts,
-                                         kernels=OracleKernels(scores))
-    stats = ranking.host_statistics(st, n_posts, want_auc=False, kernels=OracleKernels(scores))
-    res = ranking.aggregate(stats, n_posts, want_auc=False)
+                                         kernels=OracleKernels(scores), want_auc=want_auc)
+    stats = ranking.host_statistics(st, n_posts, want_auc=want_auc, kernels=OracleKernels(scores))
+    res = ranking.aggregate(stats, n_posts, want_auc=want_auc)
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), first_rank=stats["first_rank"], n_pos=stats["n_pos"],
-             hits=stats["hits"], topk=st["topk_index"].numpy(), res=np.array([float(x) for x in res]))
+             hits=stats["hits"], topk=st["topk_index"].numpy(), res=np.array([float(x) for x in res]),
+             auc_num=stats.get("auc_num", np.zeros(0, np.int64)))
     dist.destroy_process_group()
 
 
@@ -167,3 +192,19 @@ def test_two_rank_exchange_matches_unsharded_oracle(tmp_path):
         assert got[:2] == tuple(map(float, want[:2])) and got[3:] == tuple(map(float, want[3:]))
     # make sure the count-pass branch ran for at least one brand
     assert (ost["first_rank"] >= k).any()
+
+
+def test_two_rank_exchange_with_auc_matches_unsharded_oracle(tmp_path):
+    """want_auc: positives' scores ride in the exchange, every rank sweeps its own posts against the job-wide sorted
+    positives, numerators and first-positive counts are summed -> the full reference 8-tuple, bit for bit."""
+    world, k = 2, 64
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, k, str(tmp_path), True), nprocs=world, join=True)
+    scores, lab = _problem()
+    ost = oref.rank_stats(scores, lab)
+    want = tuple(map(float, oref.rank_metrics_vec(scores, lab)))
+    for rank in range(world):
+        g = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
+        assert np.array_equal(g["auc_num"], ost["auc_num"])
+        assert np.array_equal(g["first_rank"], ost["first_rank"])
+        assert tuple(g["res"]) == want

@@ -32,5 +32,17 @@ if rank == 0:
           and np.array_equal(hs["n_pos"], hr["n_pos"]) and tuple(map(float, res[:2] + res[3:])) == tuple(map(float, rres[:2] + rres[3:])))
     print("sharded(%d ranks) == single GPU: %s ; result %s" % (world, ok, [float(x) for x in res]))
     assert ok
+# full 8-tuple incl. exact AUC across the shards
+st = sharded.sharded_rank_statistics(a, b_local, lab_local, d, k, n, want_auc=True)
+hs = ranking.host_statistics(st, n, want_auc=True)
+res = ranking.aggregate(hs, n, want_auc=True)
+if rank == 0:
+    ref = ranking.device_rank_statistics(a, b_full, labels.to(dev, torch.int32), d, k=k, want_auc=True)
+    hr = ranking.host_statistics(ref, n, want_auc=True)
+    rres = ranking.aggregate(hr, n, want_auc=True)
+    ok = (np.array_equal(hs["auc_num"], hr["auc_num"]) and np.array_equal(hs["first_rank"], hr["first_rank"])
+          and tuple(map(float, res)) == tuple(map(float, rres)))
+    print("sharded AUC (%d ranks) == single GPU: %s ; AUC %.6f" % (world, ok, float(res[2])))
+    assert ok
 dist.barrier()
 dist.destroy_process_group()
