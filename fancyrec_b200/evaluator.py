@@ -102,3 +102,31 @@ def test_post_ranking(brand_num, metric, model, post_embs, brands):
 
 
 test_post_ranking.__test__ = False   # not a pytest test
+
+
+def test_post_ranking_sharded(brand_num, metric, model, post_embs_local, brands_local, n_posts_total=None, group=None):
+    """test_post_ranking for a job whose posts are sharded over the ranks of a torch.distributed group (one process
+    per GPU; rank r holds the contiguous post range sharded.shard_bounds(n_posts_total, world, r)).  Returns on every
+    rank the SAME 8-tuple the single-GPU call returns for the concatenated posts, exact AUC included: one packed
+    all-gather of candidate lists / label statistics / labels / positives' scores, then two NB-length all-reduces."""
+    if metric != 'auc':
+        return None
+    import torch.distributed as dist
+    from . import sharded
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if n_posts_total is None:
+        n = torch.tensor([post_embs_local.shape[0]], dtype=torch.int64, device=post_embs_local.device)
+        if world > 1:
+            dist.all_reduce(n, group=group)
+        n_posts_total = int(n.item())
+    brand = brand_matrix(model, brand_num)
+    d = ranking.contraction_depth(post_embs_local.shape[1])
+    brand_op = ranking.to_operand(brand, side=ranking.BRAND_SIDE)
+    post_op = ranking.to_operand(post_embs_local.contiguous().float(), side=ranking.POST_SIDE)
+    st = sharded.sharded_rank_statistics(brand_op, post_op, brands_local.to(torch.int32).contiguous(), d,
+                                         ranking.MIN_TOPK, n_posts_total, group=group, want_auc=True)
+    stats = ranking.host_statistics(st, n_posts_total, want_auc=True)
+    return ranking.aggregate(stats, n_posts_total, want_auc=True)
+
+
+test_post_ranking_sharded.__test__ = False

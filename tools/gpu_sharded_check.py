@@ -44,5 +44,22 @@ if rank == 0:
           and tuple(map(float, res)) == tuple(map(float, rres)))
     print("sharded AUC (%d ranks) == single GPU: %s ; AUC %.6f" % (world, ok, float(res[2])))
     assert ok
+# the reference-facing sharded call
+import types
+from fancyrec_b200 import evaluator, model as fmodel
+opt = types.SimpleNamespace(brand_num=nb, common_embedding_size=d, brand_aspect=16)
+ba = fmodel.BrandAspects(opt).to(dev)
+with torch.no_grad():
+    gg = torch.Generator(device="cpu").manual_seed(9)
+    ba.brand_embeddings.weight.copy_(torch.randn(nb + 1, 16, generator=gg))
+    ba.aspects_embeddings.copy_(torch.randn(16, d, generator=gg))
+mdl = types.SimpleNamespace(brand_encoding=ba, opt=opt)
+lab_ok = labels.clamp(max=nb - 1)
+got = evaluator.test_post_ranking_sharded(nb, 'auc', mdl, posts[lo:hi].to(dev), lab_ok[lo:hi].to(dev))
+if rank == 0:
+    want = evaluator.test_post_ranking(nb, 'auc', mdl, posts.to(dev), lab_ok.to(dev))
+    ok = tuple(map(float, got)) == tuple(map(float, want))
+    print("evaluator.test_post_ranking_sharded (%d ranks) == test_post_ranking: %s ; %s" % (world, ok, [round(float(x), 6) for x in got]))
+    assert ok
 dist.barrier()
 dist.destroy_process_group()
