@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(256) sort_segments_kernel(const int64_t* __res
 }
 
 // ---- exact AUC numerator + "posts before the first positive" from dense score rows ---------
-constexpr int kAucChunk = 8192;   // positives staged in shared memory per sweep (32 KB)
-constexpr int kAucBuckets = 1024; // coarse score -> first-guess index table (exactness comes from the fix-up scan)
+constexpr int kAucChunk = 4096;   // positives staged in shared memory per sweep (16 KB)
+constexpr int kAucBuckets = 4096; // score -> index table; entries whose neighbourhood holds no positive are exact as is
 
 __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__ scores, int64_t ld, int row0,
                                                        int64_t n_posts, const int32_t* __restrict__ labels,
@@ -220,6 +220,26 @@ __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__
       guess[q] = inv_w > 0.f ? lo : 0;
     }
     __syncthreads();
+    // Fast-path flags.  The bucket index computed for a score can be off by one against the edges used above, so
+    // guess[q] is the exact answer for every score that lands in bucket q iff no positive lies between edge[q-1] and
+    // edge[q+2]; such entries keep their sign bit clear, the others get it set and go through the fix-up scan.  Bucket
+    // arithmetic is only trusted when a bucket is much wider than the rounding of a score (else: all flagged).
+    {
+      const float width = (hi_s - lo_s) / (float)kAucBuckets;
+      const float mag = fmaxf(fabsf(lo_s), fabsf(hi_s));
+      const bool trust = inv_w > 0.f && width >= 64.f * mag * 1.1920929e-7f && width > 0.f;
+      unsigned int flags = 0;                      // <= 17 entries per thread
+      int t = 0;
+      for (int q = threadIdx.x; q <= kAucBuckets; q += blockDim.x, ++t) {
+        const int qa = q > 0 ? q - 1 : 0, qb = q + 2 < kAucBuckets ? q + 2 : kAucBuckets;
+        if (!trust || guess[qa] != guess[qb]) flags |= 1u << t;
+      }
+      __syncthreads();
+      t = 0;
+      for (int q = threadIdx.x; q <= kAucBuckets; q += blockDim.x, ++t)
+        if ((flags >> t) & 1u) guess[q] |= (int)0x80000000;
+    }
+    __syncthreads();
     // 8 independent (score, label) loads in flight per thread: the sweep is latency-bound otherwise
     constexpr int U = 8;
     unsigned int auc32 = 0, before32 = 0;      // per-batch partials stay 32-bit; folded into u64 per batch
@@ -246,13 +266,16 @@ __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__
           int q = (int)((s - lo_s) * inv_w);
           q = q < 0 ? 0 : (q > kAucBuckets ? kAucBuckets : q);
           idx = guess[q];
-          int steps = 0;
-          while (idx < m && spos[idx] <= s && steps < 8) { ++idx; ++steps; }
-          while (idx > 0 && spos[idx - 1] > s && steps < 8) { --idx; ++steps; }
-          if (steps >= 8) {                      // crowded bucket (ties / clustered positives): exact binary search
-            int lo = 0, hi = m;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (spos[mid] > s) hi = mid; else lo = mid + 1; }
-            idx = lo;
+          if (idx < 0) {                           // a positive nearby: fix the guess up exactly
+            idx &= 0x7FFFFFFF;
+            int steps = 0;
+            while (idx < m && spos[idx] <= s && steps < 8) { ++idx; ++steps; }
+            while (idx > 0 && spos[idx - 1] > s && steps < 8) { --idx; ++steps; }
+            if (steps >= 8) {                      // crowded bucket (ties / clustered positives): exact binary search
+              int lo = 0, hi = m;
+              while (lo < hi) { const int mid = (lo + hi) >> 1; if (spos[mid] > s) hi = mid; else lo = mid + 1; }
+              idx = lo;
+            }
           }
         }
         auc32 += (unsigned int)(m - idx);
