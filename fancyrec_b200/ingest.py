@@ -20,6 +20,25 @@ def _is_pinned_tensor(x):
     return isinstance(x, torch.Tensor) and not x.is_cuda and x.is_pinned()
 
 
+def chunk_bounds(n_posts, row_ptr, chunk_posts):
+    """Cut posts 0..n_posts into consecutive chunks of at most `chunk_posts` posts; with a CSR `row_ptr` (pooled posts) a
+    chunk is also bounded in frame ROWS (chunk_posts rows, or one post if a single post has more) so that the staging
+    buffers stay small.  Returns (bounds, max_rows): chunk c is posts bounds[c] .. bounds[c+1]-1."""
+    bounds = [0]
+    if row_ptr is None:
+        while bounds[-1] < n_posts:
+            bounds.append(min(n_posts, bounds[-1] + chunk_posts))
+        return bounds, min(chunk_posts, n_posts)
+    row_ptr = np.asarray(row_ptr, dtype=np.int64)
+    row_budget = max(chunk_posts, int((row_ptr[1:] - row_ptr[:-1]).max())) if n_posts else chunk_posts
+    while bounds[-1] < n_posts:
+        p0 = bounds[-1]
+        p1 = int(np.searchsorted(row_ptr, row_ptr[p0] + row_budget, side="right")) - 1
+        bounds.append(min(n_posts, max(p0 + 1, min(p1, p0 + chunk_posts))))
+    max_rows = max([int(row_ptr[b1] - row_ptr[b0]) for b0, b1 in zip(bounds[:-1], bounds[1:])] + [0])
+    return bounds, max_rows
+
+
 class _Stager:
     """Two pinned host buffers + two device buffers of `rows` x `cols` fp32 and the events that guard them."""
 
@@ -68,20 +87,8 @@ def finalize_from_host(visual, text=None, row_ptr=None, row_idx=None, visual_nor
     if n_posts == 0:
         return out_f32, out_bf16
 
-    # chunk boundaries in posts; a pooled chunk is also bounded in ROWS so that the staging buffers stay small
     chunk_posts = max(1, int(chunk_posts))
-    bounds = [0]
-    if row_ptr is None:
-        while bounds[-1] < n_posts:
-            bounds.append(min(n_posts, bounds[-1] + chunk_posts))
-        max_rows = chunk_posts
-    else:
-        row_budget = max(chunk_posts, int((row_ptr[1:] - row_ptr[:-1]).max()))
-        while bounds[-1] < n_posts:
-            p0 = bounds[-1]
-            p1 = int(np.searchsorted(row_ptr, row_ptr[p0] + row_budget, side="right")) - 1
-            bounds.append(min(n_posts, max(p0 + 1, min(p1, p0 + chunk_posts))))
-        max_rows = max(int(row_ptr[b1] - row_ptr[b0]) for b0, b1 in zip(bounds[:-1], bounds[1:]))
+    bounds, max_rows = chunk_bounds(n_posts, row_ptr, chunk_posts)
     direct_v = _is_pinned_tensor(visual) and row_idx is None
     direct_t = text is None or _is_pinned_tensor(text)
     sv = _Stager(max(max_rows, 1), dv, device, not direct_v)
