@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(256) softmax_pool_kernel(const float* __restri
   __syncthreads();
   z = 0.f;
   for (int w = 0; w < 8; ++w) z += red[w];
-  const float inv = 1.0f / (z * (float)t_max);
+  const float inv = len > 0 ? 1.0f / (z * (float)t_max) : 0.f;     // an empty sequence gives a zero row (all weights 0)
   const float* xb = x + (int64_t)b * t_max * d;
   float* ob = out + (int64_t)b * d;
   if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {

@@ -305,10 +305,12 @@ def test_masked_softmax_pool_matches_reference_loop():
         x = rs.standard_normal((b, t, d)).astype(np.float32)
         att = (3 * rs.standard_normal((b, t, 1))).astype(np.float32)
         lengths = rs.randint(1, t + 1, b)
-        lengths[0], lengths[1] = t, 1
+        lengths[0], lengths[1], lengths[2] = t, 1, 0               # full, single step, empty (-> zero row)
         got = ops.masked_softmax_pool(to_dev(x), to_dev(att), lengths.tolist()).cpu().numpy()
         want = np.zeros((b, d))
         for i in range(b):
+            if lengths[i] == 0:
+                continue
             a = att[i, :lengths[i], 0].astype(np.float64)
             w = np.exp(a - a.max()); w /= w.sum()
             weight = np.zeros(t); weight[:lengths[i]] = w
