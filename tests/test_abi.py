@@ -109,3 +109,28 @@ def test_vectorised_aggregate_is_bit_identical_to_per_brand_reference_calls():
         got = ranking.aggregate(st, n_posts, True)
         want = oref.aggregate(st, n_posts)
         assert tuple(map(float, got)) == tuple(map(float, want))
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/frx.h is the drop-in boundary: it must compile as C99 (no C++ / torch types in the signatures) and a plain
+    C program must link against libfrx_b200.so and call it (no compute without a GPU: only the version query)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "c_check.c"
+    src.write_text('#include "frx.h"\n#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '  size_t ws = frx_score_topk_workspace_bytes(1000, 1000000, 3072, 100);\n'
+                   '  printf("%d %d\\n", frx_abi_version(), ws > 0);\n'
+                   '  return frx_device_check(0) == 0 ? 0 : 3;   /* 3 on a box without an sm_100 GPU */\n}\n')
+    exe = tmp_path / "c_check"
+    libdir = os.path.join(root, "fancyrec_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-l:libfrx_b200.so", "-Wl,-rpath," + libdir], check=True)
+    p = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True)
+    assert p.stdout.split() == ["1", "1"]
+    import torch
+    assert p.returncode == (0 if torch.cuda.is_available() else 3)
