@@ -178,8 +178,9 @@ __global__ void __launch_bounds__(256) sort_segments_kernel(const int64_t* __res
 }
 
 // ---- exact AUC numerator + "posts before the first positive" from dense score rows ---------
-constexpr int kAucChunk = 4096;   // positives staged in shared memory per sweep (16 KB)
-constexpr int kAucBuckets = 4096; // score -> index table; entries whose neighbourhood holds no positive are exact as is
+constexpr int kAucChunk = 4000;     // positives staged in shared memory per sweep (16 KB; static shared memory stays < 48 KB)
+constexpr int kAucBuckets = 16383;  // score bucket -> number of positives at or below its lower edge (uint16, 32 KB)
+constexpr int kAucWindow = 4;       // positives compared inline around a bucket; more than that -> binary search
 
 __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__ scores, int64_t ld, int row0,
                                                        int64_t n_posts, const int32_t* __restrict__ labels,
@@ -189,8 +190,8 @@ __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__
                                                        const int32_t* __restrict__ best_index, int64_t index_base,
                                                        unsigned long long* __restrict__ auc_num,
                                                        unsigned long long* __restrict__ before_first) {
-  __shared__ float spos[kAucChunk];
-  __shared__ int guess[kAucBuckets + 1];
+  __shared__ float spos[kAucChunk + kAucWindow];       // padded with +inf: the inline window never reads garbage
+  __shared__ unsigned short guess[kAucBuckets + 1];
   __shared__ unsigned long long red[2][8];
   const int r = blockIdx.x;
   const int b = row0 + r;
@@ -198,46 +199,31 @@ __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__
   const int64_t p0 = seg_ptr[b], np = seg_ptr[b + 1] - p0;
   if (np == 0) return;
   const float bs = best_score[b];
-  const int64_t bi = best_index[b];
+  const int bi = best_index[b];
   const float* row = scores + (int64_t)r * ld;
   unsigned long long auc = 0ull, before = 0ull;
   for (int64_t ch = 0; ch < np; ch += kAucChunk) {
     const int m = (int)((np - ch) < kAucChunk ? (np - ch) : kAucChunk);
     __syncthreads();
-    for (int i = threadIdx.x; i < m; i += blockDim.x) spos[i] = pos_sorted[p0 + ch + i];
+    for (int i = threadIdx.x; i < m + kAucWindow; i += blockDim.x) spos[i] = i < m ? pos_sorted[p0 + ch + i] : INFINITY;
     __syncthreads();
-    // guess[q] = upper_bound(spos, lower edge of bucket q): a negative score s in bucket q has its exact
-    // upper_bound at or after guess[q]; the scan below fixes the guess up in both directions, so the bucket
-    // arithmetic never affects the result, only the number of steps (typically 0-2 instead of log2(m)).
+    // guess[q] = #{positives <= lower edge of bucket q}.  A score s that the bucket arithmetic puts in bucket q lies,
+    // rounding included, between edge[q-1] and edge[q+2]; so #{positives <= s} = guess[q-1] + the number of positives
+    // among spos[guess[q-1] .. guess[q+2]) that are <= s -- at most kAucWindow inline compares when that window is
+    // small (almost always: 16 k buckets for <= 4096 positives), a binary search inside the window otherwise.  The
+    // result is exact either way; the table only bounds the work.  Bucket arithmetic is trusted only when a bucket
+    // is much wider than the rounding of a score (else every score takes the full binary search).
     const float lo_s = spos[0], hi_s = spos[m - 1];
     const float inv_w = (hi_s > lo_s) ? (float)kAucBuckets / (hi_s - lo_s) : 0.f;
+    const float width = (hi_s - lo_s) / (float)kAucBuckets;
+    const bool trust = inv_w > 0.f && width > 0.f && width >= 64.f * fmaxf(fabsf(lo_s), fabsf(hi_s)) * 1.1920929e-7f;
     for (int q = threadIdx.x; q <= kAucBuckets; q += blockDim.x) {
-      const float edge = lo_s + (float)q / inv_w;
       int lo = 0, hi = m;
-      if (inv_w > 0.f) {
+      if (trust) {
+        const float edge = lo_s + (float)q / inv_w;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (spos[mid] > edge) hi = mid; else lo = mid + 1; }
       }
-      guess[q] = inv_w > 0.f ? lo : 0;
-    }
-    __syncthreads();
-    // Fast-path flags.  The bucket index computed for a score can be off by one against the edges used above, so
-    // guess[q] is the exact answer for every score that lands in bucket q iff no positive lies between edge[q-1] and
-    // edge[q+2]; such entries keep their sign bit clear, the others get it set and go through the fix-up scan.  Bucket
-    // arithmetic is only trusted when a bucket is much wider than the rounding of a score (else: all flagged).
-    {
-      const float width = (hi_s - lo_s) / (float)kAucBuckets;
-      const float mag = fmaxf(fabsf(lo_s), fabsf(hi_s));
-      const bool trust = inv_w > 0.f && width >= 64.f * mag * 1.1920929e-7f && width > 0.f;
-      unsigned int flags = 0;                      // <= 17 entries per thread
-      int t = 0;
-      for (int q = threadIdx.x; q <= kAucBuckets; q += blockDim.x, ++t) {
-        const int qa = q > 0 ? q - 1 : 0, qb = q + 2 < kAucBuckets ? q + 2 : kAucBuckets;
-        if (!trust || guess[qa] != guess[qb]) flags |= 1u << t;
-      }
-      __syncthreads();
-      t = 0;
-      for (int q = threadIdx.x; q <= kAucBuckets; q += blockDim.x, ++t)
-        if ((flags >> t) & 1u) guess[q] |= (int)0x80000000;
+      guess[q] = (unsigned short)(trust ? lo : 0);
     }
     __syncthreads();
     // 8 independent (score, label) loads in flight per thread: the sweep is latency-bound otherwise
@@ -252,35 +238,40 @@ __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__
         sv[u] = j < c1 ? __ldg(row + j) : 0.f;
         lv[u] = j < c1 ? __ldg(labels + j) : b;          // out of range: treated as a positive -> skipped
       }
+      const int g0idx = (int)(index_base + j0);          // global post index of sv[0]; fits int32 (checked by the caller)
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int64_t j = j0 + (int64_t)u * blockDim.x;
+        const bool in_range = j0 + (int64_t)u * blockDim.x < c1;
         const float s = sv[u];
-        if (ch == 0 && j < c1) before32 += ((s > bs) || (s == bs && (index_base + j) < bi)) ? 1u : 0u;
+        if (ch == 0 && in_range)
+          before32 += ((s > bs) || (s == bs && (g0idx + u * (int)blockDim.x) < bi)) ? 1u : 0u;
         if (lv[u] == b) continue;              // negatives only (evaluator.py:112)
-        // number of positives e in this chunk with e > s  ==  m - upper_bound(spos, s)
+        // number of positives e in this chunk with e > s  ==  m - #{positives <= s}
         int idx;
         if (!(s >= lo_s)) idx = 0;             // below every positive (or NaN)
         else if (s >= hi_s) idx = m;           // at or above every positive
         else {
-          int q = (int)((s - lo_s) * inv_w);
-          q = q < 0 ? 0 : (q > kAucBuckets ? kAucBuckets : q);
-          idx = guess[q];
-          if (idx < 0) {                           // a positive nearby: fix the guess up exactly
-            idx &= 0x7FFFFFFF;
-            int steps = 0;
-            while (idx < m && spos[idx] <= s && steps < 8) { ++idx; ++steps; }
-            while (idx > 0 && spos[idx - 1] > s && steps < 8) { --idx; ++steps; }
-            if (steps >= 8) {                      // crowded bucket (ties / clustered positives): exact binary search
-              int lo = 0, hi = m;
-              while (lo < hi) { const int mid = (lo + hi) >> 1; if (spos[mid] > s) hi = mid; else lo = mid + 1; }
-              idx = lo;
-            }
+          int lo, hi;
+          if (trust) {
+            int q = (int)((s - lo_s) * inv_w);
+            q = q < 0 ? 0 : (q > kAucBuckets ? kAucBuckets : q);
+            lo = guess[q > 0 ? q - 1 : 0];
+            hi = guess[q + 2 < kAucBuckets ? q + 2 : kAucBuckets];
+          } else {
+            lo = 0; hi = m;
+          }
+          if (hi - lo <= kAucWindow) {
+            idx = lo;
+#pragma unroll
+            for (int i = 0; i < kAucWindow; ++i) idx += (lo + i < hi && spos[lo + i] <= s) ? 1 : 0;
+          } else {                             // crowded window (ties / clustered positives): exact binary search
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (spos[mid] > s) hi = mid; else lo = mid + 1; }
+            idx = lo;
           }
         }
         auc32 += (unsigned int)(m - idx);
       }
-      auc += auc32; before += before32;          // <= 8 * 8192 per batch: no 32-bit overflow
+      auc += auc32; before += before32;          // <= 8 * 4096 per batch: no 32-bit overflow
       auc32 = 0; before32 = 0;
     }
   }
