@@ -10,6 +10,7 @@ instead of an open+seek+fromfile per row.  `rows` / `read_matrix` / `read_csr` a
 they return index arrays (or the matrix) so that the whole gather + mean-pool + normalise happens in ONE
 device pass (frx_finalize_posts with row_ptr / row_idx) instead of 94 posts/s of Python lists.
 """
+import itertools
 import os
 
 import numpy as np
@@ -59,7 +60,8 @@ class ImageBigFile:
         fancyrec_b200.ops.finalize_posts(row_ptr=..., row_idx=...)."""
         counts = np.fromiter((len(f) for f in frame_names_per_post), dtype=np.int64, count=len(frame_names_per_post))
         row_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-        row_idx = np.fromiter((self.name2index[n] for frames in frame_names_per_post for n in frames),
+        # C-level iteration (chain + bound dict lookup): ~3x the rate of a Python generator expression
+        row_idx = np.fromiter(map(self.name2index.__getitem__, itertools.chain.from_iterable(frame_names_per_post)),
                               dtype=np.int32, count=int(row_ptr[-1]))
         return row_idx, row_ptr
 
