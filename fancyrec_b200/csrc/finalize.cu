@@ -736,8 +736,12 @@ int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_
   int grid = (int)(n_posts < (int64_t)num_sms() * 8 ? n_posts : (int64_t)num_sms() * 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (vec && (d > 2048 || (d > 1024 && row_ptr == nullptr)) && d <= 4096 && ld_bf16 % 4 == 0) {   // long rows: block per row
+    // One resident wave of whole blocks per SM, measured per variant (tools/gpu_finalize_grid.py: bandwidth vs blocks per
+    // SM): 4 per SM for the 3072-wide un-pooled rows (2.73 ms against 2.96 ms with 8 per SM queued as two partial waves),
+    // 5 per SM for the 2048-wide rows and the pooled rows.  Grid-stride loops cover the rest.
+    const bool wide_unpooled = row_ptr == nullptr && d > 2048;
     int64_t blocks = n_posts;
-    const int64_t max_blocks = (int64_t)num_sms() * 8;
+    const int64_t max_blocks = (int64_t)num_sms() * (wide_unpooled || d > 3072 ? 4 : 5);
     if (blocks > max_blocks) blocks = max_blocks;
     if (row_ptr != nullptr) {
       if (d <= 3072) finalize_block_kernel<3, true><<<(int)blocks, 256, 0, st>>>(P);
