@@ -416,7 +416,10 @@ __global__ void __launch_bounds__(256) finalize_block_kernel(FinalizeParams P) {
 template <int NV>
 static void launch_finalize_warp(const FinalizeParams& P, cudaStream_t st) {
   const int64_t warps_needed = P.n_posts;
-  const int64_t max_blocks = (int64_t)num_sms() * 8;
+  // whole blocks per SM, measured (tools/gpu_finalize_grid_warp.py): un-pooled rows of <= 1024 columns run best with
+  // 2 blocks per SM (6.9 TB/s against 6.5 TB/s with 8); pooled rows are flat from 4 per SM upwards
+  const int per_sm = (NV <= 8 && P.row_ptr == nullptr) ? 2 : 8;
+  const int64_t max_blocks = (int64_t)num_sms() * per_sm;
   int64_t blocks = (warps_needed + 7) / 8;
   if (blocks > max_blocks) blocks = max_blocks;
   finalize_warp_kernel<NV><<<(int)blocks, 256, 0, st>>>(P);
