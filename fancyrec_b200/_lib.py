@@ -9,6 +9,31 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfrx_b200.so")
+STAMP_PATH = os.path.join(_HERE, "libfrx_b200.stamp")
+CSRC = os.path.join(_HERE, "csrc")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "frx.h")
+NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+              "-lineinfo", "-cudart", "static"]
+
+
+def sources():
+    """Every translation unit of libfrx_b200.so (csrc/*.cu) and the headers they include."""
+    names = sorted(os.listdir(CSRC))
+    return [n for n in names if n.endswith(".cu")], [n for n in names if n.endswith(".cuh")]
+
+
+def source_hash():
+    """Hash of everything libfrx_b200.so is built from; __graft_entry__.build() writes it next to the library and
+    load() refuses a library whose stamp differs (a stale binary would silently run old kernels)."""
+    import hashlib
+    h = hashlib.sha256()
+    cu, cuh = sources()
+    for name in cu + cuh:
+        h.update(name.encode())
+        h.update(open(os.path.join(CSRC, name), "rb").read())
+    h.update(open(HEADER, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
 
 c_i32, c_i64, c_f32, c_sz, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t, ctypes.c_void_p
 
@@ -71,6 +96,12 @@ def load():
         raise FrxError(
             "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(fancyrec_b200 has no CPU fallback)" % LIB_PATH)
+    if os.environ.get("FRX_SKIP_STAMP_CHECK") != "1":
+        have = open(STAMP_PATH).read().strip() if os.path.exists(STAMP_PATH) else "(no stamp)"
+        want = source_hash()
+        if have != want:
+            raise FrxError("%s is stale: built from sources %s, tree is %s -- rebuild with "
+                           "`python -c 'import __graft_entry__ as g; g.build()'`" % (LIB_PATH, have[:12], want[:12]))
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)

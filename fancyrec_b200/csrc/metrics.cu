@@ -178,9 +178,24 @@ __global__ void __launch_bounds__(256) sort_segments_kernel(const int64_t* __res
 }
 
 // ---- exact AUC numerator + "posts before the first positive" from dense score rows ---------
-constexpr int kAucChunk = 4000;     // positives staged in shared memory per sweep (16 KB; static shared memory stays < 48 KB)
-constexpr int kAucBuckets = 16383;  // score bucket -> number of positives at or below its lower edge (uint16, 32 KB)
-constexpr int kAucWindow = 4;       // positives compared inline around a bucket; more than that -> binary search
+// evaluator.py:111-113: sum over the brand's positives e of #{negatives el : e > el}, i.e. for every negative score s
+// the number of the brand's positives above it, m - #{positives <= s}.  One block streams a row of scores once; the
+// brand's sorted positives sit in shared memory behind a bucket table:
+//   bucket(x) = min(Q-1, (int)((x - lo) * inv_w))        (lo / hi = smallest / largest positive of the chunk)
+// is evaluated with the SAME fp32 instruction sequence for positives and for scores, and every step of it (correctly
+// rounded subtract, multiply by a positive constant, truncation, clamp) is monotone non-decreasing.  Hence
+// bucket(s) > bucket(p) implies s > p and bucket(s) < bucket(p) implies s < p: for a score in bucket q,
+//   #{positives <= s} = #{p : bucket(p) < q} + #{p in bucket q : p <= s}
+// EXACTLY -- no rounding margin is needed, and only the (at most m of Q) buckets that hold a positive cost compares.
+// table[q] = #{p : bucket(p) < q} | (#{p : bucket(p) == q} << 16).
+constexpr int kAucChunk = 4000;     // positives staged in shared memory per sweep (16 KB)
+constexpr int kAucBuckets = 8192;   // 32 KB table: with the positives 48 KB per block, 4 blocks per SM
+constexpr int kAucLinear = 8;       // positives compared one by one inside a bucket; more than that -> binary search
+
+__device__ __forceinline__ int auc_bucket(float x, float lo, float inv_w) {
+  const int q = (int)__fmul_rn(__fsub_rn(x, lo), inv_w);
+  return q < kAucBuckets - 1 ? q : kAucBuckets - 1;
+}
 
 __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__ scores, int64_t ld, int row0,
                                                        int64_t n_posts, const int32_t* __restrict__ labels,
@@ -190,8 +205,9 @@ __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__
                                                        const int32_t* __restrict__ best_index, int64_t index_base,
                                                        unsigned long long* __restrict__ auc_num,
                                                        unsigned long long* __restrict__ before_first) {
-  __shared__ float spos[kAucChunk + kAucWindow];       // padded with +inf: the inline window never reads garbage
-  __shared__ unsigned short guess[kAucBuckets + 1];
+  extern __shared__ uint32_t auc_smem[];
+  uint32_t* table = auc_smem;                                             // [kAucBuckets]
+  float* spos = reinterpret_cast<float*>(auc_smem + kAucBuckets);          // [kAucChunk + 1], +inf sentinel behind the last
   __shared__ unsigned long long red[2][8];
   const int r = blockIdx.x;
   const int b = row0 + r;
@@ -205,25 +221,24 @@ __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__
   for (int64_t ch = 0; ch < np; ch += kAucChunk) {
     const int m = (int)((np - ch) < kAucChunk ? (np - ch) : kAucChunk);
     __syncthreads();
-    for (int i = threadIdx.x; i < m + kAucWindow; i += blockDim.x) spos[i] = i < m ? pos_sorted[p0 + ch + i] : INFINITY;
+    for (int i = threadIdx.x; i <= m; i += blockDim.x) spos[i] = i < m ? pos_sorted[p0 + ch + i] : INFINITY;
     __syncthreads();
-    // guess[q] = #{positives <= lower edge of bucket q}.  A score s that the bucket arithmetic puts in bucket q lies,
-    // rounding included, between edge[q-1] and edge[q+2]; so #{positives <= s} = guess[q-1] + the number of positives
-    // among spos[guess[q-1] .. guess[q+2]) that are <= s -- at most kAucWindow inline compares when that window is
-    // small (almost always: 16 k buckets for <= 4096 positives), a binary search inside the window otherwise.  The
-    // result is exact either way; the table only bounds the work.  Bucket arithmetic is trusted only when a bucket
-    // is much wider than the rounding of a score (else every score takes the full binary search).
     const float lo_s = spos[0], hi_s = spos[m - 1];
-    const float inv_w = (hi_s > lo_s) ? (float)kAucBuckets / (hi_s - lo_s) : 0.f;
-    const float width = (hi_s - lo_s) / (float)kAucBuckets;
-    const bool trust = inv_w > 0.f && width > 0.f && width >= 64.f * fmaxf(fabsf(lo_s), fabsf(hi_s)) * 1.1920929e-7f;
-    for (int q = threadIdx.x; q <= kAucBuckets; q += blockDim.x) {
+    // hi == lo (one positive, or all tied): no score is routed through the table (see the range tests below)
+    const float inv_w = hi_s > lo_s ? (float)kAucBuckets / (hi_s - lo_s) : 0.f;
+    {
+      // thread t owns buckets [q0, q1): the first positive whose bucket is >= q0 by binary search (bucket() is monotone
+      // over the sorted positives), then one walk over its buckets
+      constexpr int per = kAucBuckets / 256;
+      const int q0 = threadIdx.x * per;
       int lo = 0, hi = m;
-      if (trust) {
-        const float edge = lo_s + (float)q / inv_w;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (spos[mid] > edge) hi = mid; else lo = mid + 1; }
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (auc_bucket(spos[mid], lo_s, inv_w) >= q0) hi = mid; else lo = mid + 1; }
+      int i = lo;
+      for (int q = q0; q < q0 + per; ++q) {
+        const int first = i;
+        while (i < m && auc_bucket(spos[i], lo_s, inv_w) == q) ++i;
+        table[q] = (uint32_t)first | ((uint32_t)(i - first) << 16);
       }
-      guess[q] = (unsigned short)(trust ? lo : 0);
     }
     __syncthreads();
     // 8 independent (score, label) loads in flight per thread: the sweep is latency-bound otherwise
@@ -235,10 +250,10 @@ __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t j = j0 + (int64_t)u * blockDim.x;
-        sv[u] = j < c1 ? __ldg(row + j) : 0.f;
-        lv[u] = j < c1 ? __ldg(labels + j) : b;          // out of range: treated as a positive -> skipped
+        sv[u] = j < c1 ? __ldcs(row + j) : 0.f;            // streamed once: evict first, the labels stay in L2
+        lv[u] = j < c1 ? __ldg(labels + j) : b;            // out of range: treated as a positive -> skipped
       }
-      const int g0idx = (int)(index_base + j0);          // global post index of sv[0]; fits int32 (checked by the caller)
+      const int g0idx = (int)(index_base + j0);            // global post index of sv[0]; fits int32 (checked by the caller)
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const bool in_range = j0 + (int64_t)u * blockDim.x < c1;
@@ -246,25 +261,18 @@ __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__
         if (ch == 0 && in_range)
           before32 += ((s > bs) || (s == bs && (g0idx + u * (int)blockDim.x) < bi)) ? 1u : 0u;
         if (lv[u] == b) continue;              // negatives only (evaluator.py:112)
-        // number of positives e in this chunk with e > s  ==  m - #{positives <= s}
+        // idx = #{positives of this chunk <= s}; the negative adds m - idx
         int idx;
-        if (!(s >= lo_s)) idx = 0;             // below every positive (or NaN)
-        else if (s >= hi_s) idx = m;           // at or above every positive
+        if (!(s < hi_s)) idx = m;                           // at or above every positive; NaN: `e > NaN` is False for every e
+        else if (s < lo_s) idx = 0;                         // below every positive
         else {
-          int lo, hi;
-          if (trust) {
-            int q = (int)((s - lo_s) * inv_w);
-            q = q < 0 ? 0 : (q > kAucBuckets ? kAucBuckets : q);
-            lo = guess[q > 0 ? q - 1 : 0];
-            hi = guess[q + 2 < kAucBuckets ? q + 2 : kAucBuckets];
-          } else {
-            lo = 0; hi = m;
-          }
-          if (hi - lo <= kAucWindow) {
-            idx = lo;
-#pragma unroll
-            for (int i = 0; i < kAucWindow; ++i) idx += (lo + i < hi && spos[lo + i] <= s) ? 1 : 0;
-          } else {                             // crowded window (ties / clustered positives): exact binary search
+          const uint32_t t = table[auc_bucket(s, lo_s, inv_w)];
+          idx = (int)(t & 0xFFFFu);
+          int n = (int)(t >> 16);
+          if (n <= kAucLinear) {
+            while (n > 0 && spos[idx] <= s) { ++idx; --n; }
+          } else {                             // crowded bucket (ties / clustered positives): binary search inside it
+            int lo = idx, hi = idx + n;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (spos[mid] > s) hi = mid; else lo = mid + 1; }
             idx = lo;
           }
@@ -456,13 +464,17 @@ int frx_auc_rows(const float* scores, int64_t ld, int row0, int n_rows, int64_t 
   FRX_CHECK_ARG(scores && labels && seg_ptr && pos_sorted && best_score && best_index && auc_num && before_first,
                 "frx_auc_rows: NULL pointer");
   FRX_CHECK_ARG(n_rows > 0 && n_posts > 0 && ld >= n_posts && row0 >= 0, "frx_auc_rows: bad sizes");
-  int64_t ysplit = ((int64_t)num_sms() * 4 + n_rows - 1) / n_rows;
-  const int64_t max_split = (n_posts + 4095) / 4096;
+  // ~8 blocks per resident slot (4 per SM): short enough for the block scheduler to even out the tail, long enough
+  // (>= 32 k scores) that rebuilding the row's bucket table per block stays a few percent
+  int64_t ysplit = ((int64_t)num_sms() * 32 + n_rows - 1) / n_rows;
+  const int64_t max_split = (n_posts + 32767) / 32768;
   if (ysplit > max_split) ysplit = max_split;
   if (ysplit < 1) ysplit = 1;
   if (ysplit > 65535) ysplit = 65535;
   dim3 grid(n_rows, (unsigned)ysplit);
-  auc_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(scores, ld, row0, n_posts, labels, seg_ptr, pos_sorted,
+  const size_t smem = (size_t)kAucBuckets * sizeof(uint32_t) + (size_t)(kAucChunk + 1) * sizeof(float);
+  FRX_CUDA(cudaFuncSetAttribute(auc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auc_rows_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(scores, ld, row0, n_posts, labels, seg_ptr, pos_sorted,
                                                           best_score, best_index, index_base, auc_num, before_first);
   FRX_LAUNCH_CHECK();
   return FRX_OK;

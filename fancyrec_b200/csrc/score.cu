@@ -51,6 +51,13 @@ constexpr int EPI_WARP0 = 4;                 // warps 4..11: lane quarter = warp
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = (EPI_WARP0 + NUM_EPI_WARPS) * 32;   // 384
 constexpr int TMEM_COLS = 512;
+// Register budget.  The CTA is launched with KERNEL_REGS per thread (52 224 of the SM's 65 536 registers), then the
+// warp group of the TMA / MMA / TMEM warps hands its surplus to the two epilogue warp groups (setmaxnreg):
+// 128 x 72 + 256 x 168 = 384 x 136.  What the CTA leaves free -- 13 312 registers and ~20 KB of shared memory -- is
+// exactly one 256-thread block of the post-finalisation kernel (<= 52 registers), so the HBM-bound finalisation of the
+// NEXT batch can run on the same SMs, from a second stream, while this batch is contracted (pipeline.py).
+constexpr int KERNEL_REGS = 136, LEAN_REGS = 72, EPI_REGS = 168;
+static_assert(128 * LEAN_REGS + NUM_EPI_WARPS * 32 * EPI_REGS == NUM_THREADS * KERNEL_REGS, "register budget is redistributed exactly");
 constexpr int MAX_MERGE_KEYS = 16384;
 constexpr int MAX_NEED_TILES = 1024;          // COUNT mode tracks per-m-tile skip flags for up to 131072 brands
 constexpr int64_t kSampleMinPosts = 262144;   // below this the warm-up is too short to be worth a sample pass
@@ -246,6 +253,26 @@ __device__ __forceinline__ int hist_edge(const uint32_t* hrow, uint32_t k) {
   return -1;
 }
 
+// One 32-column chunk of one accumulator row -> the fp32 score matrix (DENSE mode; TOPK mode when the caller also wants
+// the scores, e.g. for the exact-AUC sweep).  STREAM: evict-first stores, so that a 4 GB score matrix written next to
+// the fused top-k pass does not push the shared post tiles out of L2.
+template <bool STREAM>
+__device__ __forceinline__ void store_dense_chunk(float* dst, const uint32_t (&v)[32], int nvalid, float sc) {
+  if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 o = make_float4(__uint_as_float(v[i]) * sc, __uint_as_float(v[i + 1]) * sc,
+                                   __uint_as_float(v[i + 2]) * sc, __uint_as_float(v[i + 3]) * sc);
+      if (STREAM) __stcs(reinterpret_cast<float4*>(dst + i), o);
+      else *reinterpret_cast<float4*>(dst + i) = o;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < nvalid) dst[i] = __uint_as_float(v[i]) * sc;
+  }
+}
+
 template <int MODE, bool TF32, bool PAIR>
 __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ScoreParams& P) {
   using R = Ring<PAIR>;
@@ -257,40 +284,44 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
   uint8_t* smem = smem_raw + (base - raw);
   SmemTail* tail = reinterpret_cast<SmemTail*>(smem + (size_t)RING_BYTES);
   const uint32_t smem_a = base, smem_b = base + STAGES * A_STAGE_BYTES;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int BK = TF32 ? 32 : 64;                      // operand elements per k-block
+  {
+    // ---- prologue (every warp, launch-time register budget) ----
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+      prefetch_tmap(&tmap_a);
+      prefetch_tmap(&tmap_b);
+      for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&tail->full[s]), 1); mbar_init(smem_u32(&tail->empty[s]), 1); }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(smem_u32(&tail->tmem_full[s]), 1);
+        mbar_init(smem_u32(&tail->tmem_empty[s]), NUM_EPI_WARPS * (PAIR ? 2 : 1));   // the leader hears both CTAs' epilogues
+      }
+      fence_barrier_init();
+    }
+    if (warp == 2) {
+      if (PAIR) tmem_alloc_pair<TMEM_COLS>(smem_u32(&tail->tmem_base));
+      else tmem_alloc<TMEM_COLS>(smem_u32(&tail->tmem_base));
+    }
+    if (MODE == MODE_COUNT) {
+      // rows without a threshold (thr_index < 0) are not counted; an m-tile made only of such rows is skipped by all
+      // three roles, so the pass costs only the m-tiles that need it (nothing at all when no first positive is missing)
+      const int nt = P.num_m_tiles < MAX_NEED_TILES ? P.num_m_tiles : MAX_NEED_TILES;
+      for (int i = threadIdx.x; i < nt; i += NUM_THREADS) tail->tile_need[i] = 0;
+      __syncthreads();
+      for (int r = threadIdx.x; r < P.nb && r < MAX_NEED_TILES * BM; r += NUM_THREADS)
+        if (__ldg(P.thr_index + r) >= 0) tail->tile_need[r / BM] = 1;
+    }
+    tc_fence_before();
+    if (PAIR) cluster_sync_all(); else __syncthreads();    // the peer's barriers are initialised before anything targets them
+    tc_fence_after();
+  }
+  const uint32_t tid = threadIdx.x, bid = blockIdx.x, nbid = gridDim.x;
+  const int warp = (int)(tid >> 5), lane = (int)(tid & 31);
   // CTA pair: cluster rank 0 = leader (issues the MMAs); the pair shares one scheduling slot and one 256-row m-unit
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
-  const int slot = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int nslots = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int slot = PAIR ? (int)(bid >> 1) : (int)bid;
+  const int nslots = PAIR ? (int)(nbid >> 1) : (int)nbid;
   const int m_units = PAIR ? (P.num_m_tiles >> 1) : P.num_m_tiles;   // the host pads num_m_tiles to even for pairs
-
-  if (threadIdx.x == 0) {
-    prefetch_tmap(&tmap_a);
-    prefetch_tmap(&tmap_b);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&tail->full[s]), 1); mbar_init(smem_u32(&tail->empty[s]), 1); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&tail->tmem_full[s]), 1);
-      mbar_init(smem_u32(&tail->tmem_empty[s]), NUM_EPI_WARPS * (PAIR ? 2 : 1));   // the leader hears both CTAs' epilogues
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) {
-    if (PAIR) tmem_alloc_pair<TMEM_COLS>(smem_u32(&tail->tmem_base));
-    else tmem_alloc<TMEM_COLS>(smem_u32(&tail->tmem_base));
-  }
-  if (MODE == MODE_COUNT) {
-    // rows without a threshold (thr_index < 0) are not counted; an m-tile made only of such rows is skipped by all
-    // three roles, so the pass costs only the m-tiles that need it (nothing at all when no first positive is missing)
-    const int nt = P.num_m_tiles < MAX_NEED_TILES ? P.num_m_tiles : MAX_NEED_TILES;
-    for (int i = threadIdx.x; i < nt; i += NUM_THREADS) tail->tile_need[i] = 0;
-    __syncthreads();
-    for (int r = threadIdx.x; r < P.nb && r < MAX_NEED_TILES * BM; r += NUM_THREADS)
-      if (__ldg(P.thr_index + r) >= 0) tail->tile_need[r / BM] = 1;
-  }
-  tc_fence_before();
-  if (PAIR) cluster_sync_all(); else __syncthreads();      // the peer's barriers are initialised before anything targets them
-  tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
 
   // item = (split * m_units + m_unit) * k_splits + ks ; a unit is one 128-row m-tile, or the pair's two m-tiles
@@ -302,8 +333,11 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
     return !(tail->tile_need[t0_] | tail->tile_need[t1_]);
   };
 
+  // Register redistribution: each role's code must be DOMINATED by its setmaxnreg -- ptxas budgets a region by the
+  // setmaxnreg that dominates it (after a merge of both it assumes the smaller budget).
   if (warp == 0) {
     // =========================== TMA producer ===========================
+    setmaxnreg_dec<LEAN_REGS>();
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int item = slot; item < n_items; item += nslots) {
@@ -343,6 +377,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
+    setmaxnreg_dec<LEAN_REGS>();
     if (lane == 0 && crank == 0) {                         // of a pair only the leader issues; its MMAs span both SMs
       constexpr int MMA_M = PAIR ? 2 * BM : BM;
       constexpr uint32_t idesc = TF32 ? make_idesc_tf32(MMA_M, BN) : make_idesc_bf16(MMA_M, BN);
@@ -358,7 +393,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
           mbar_wait(smem_u32(&tail->tmem_empty[as]), aphase ^ 1);
           tc_fence_after();
 #ifdef FRX_TRACE
-          if (P.trace && blockIdx.x == 0 && (t - t0) < 256) P.trace[(t - t0) * 4 + 0] = clock64();
+          if (P.trace && bid == 0 && (t - t0) < 256) P.trace[(t - t0) * 4 + 0] = clock64();
 #endif
           const uint32_t d_tmem = tmem_base + as * BN;
           for (int kb = kb0; kb < kb1; ++kb) {
@@ -383,7 +418,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
             if (kb == kb1 - 1) {
               if (PAIR) umma_commit_pair(smem_u32(&tail->tmem_full[as]), 3); else umma_commit(smem_u32(&tail->tmem_full[as]));
 #ifdef FRX_TRACE
-              if (P.trace && blockIdx.x == 0 && (t - t0) < 256) P.trace[(t - t0) * 4 + 1] = clock64();
+              if (P.trace && bid == 0 && (t - t0) < 256) P.trace[(t - t0) * 4 + 1] = clock64();
 #endif
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -392,8 +427,11 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
         }
       }
     }
-  } else if (warp >= EPI_WARP0) {
+  } else if (warp < EPI_WARP0) {
+    setmaxnreg_dec<LEAN_REGS>();                           // warps 2 (TMEM alloc / dealloc) and 3: same warp group as 0 and 1
+  } else {
     // =========================== epilogue ===========================
+    setmaxnreg_inc<EPI_REGS>();
     // 8 warps: lane quarter q = warp % 4 (TMEM lanes 32q..32q+31 = brand rows), column half h.
     const int q = warp & 3;
     const int h = (warp - EPI_WARP0) >> 2;
@@ -407,8 +445,8 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
       uint32_t smid; unsigned long long gt;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-      P.cta_trace[blockIdx.x * 4 + 0] = smid;
-      P.cta_trace[blockIdx.x * 4 + 1] = (long long)gt;
+      P.cta_trace[bid * 4 + 0] = smid;
+      P.cta_trace[bid * 4 + 1] = (long long)gt;
     }
 #endif
     for (int item = slot; item < n_items; item += nslots) {
@@ -470,11 +508,11 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
         if (P.cta_trace && ew == 0 && lane == 0 && item == slot && (t - t0) == 50) {
           unsigned long long gt;
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-          P.cta_trace[blockIdx.x * 4 + 2] = (long long)gt;
+          P.cta_trace[bid * 4 + 2] = (long long)gt;
         }
 #endif
 #ifdef FRX_TRACE
-        if (P.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && (t - t0) < 256) P.trace[(t - t0) * 4 + 2] = clock64();
+        if (P.trace && bid == 0 && ew == 0 && lane == 0 && (t - t0) < 256) P.trace[(t - t0) * 4 + 2] = clock64();
 #endif
 #pragma unroll 1
         for (int c = 0; c < CHUNKS; ++c) {
@@ -487,6 +525,9 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
           if (nvalid == 0) continue;                 // warp-uniform
 
           if (MODE == MODE_TOPK) {
+            // the caller also wants the score matrix (exact-AUC sweep): same accumulators, written on the way
+            if (P.dense != nullptr && row_ok)
+              store_dense_chunk<true>(P.dense + (int64_t)row * P.ld_dense + cbase, v, nvalid, 1.0f);
             if (nvalid < 32) {                       // last tile only: out-of-range columns can never qualify
 #pragma unroll
               for (int i = 0; i < 32; ++i) if (i >= nvalid) v[i] = 0x7FC00000u;   // NaN: fails every >=
@@ -560,21 +601,9 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
               }
             }
           } else if (MODE == MODE_DENSE) {
-            if (row_ok) {
-              float* dst = P.dense + (int64_t)ks * P.partial_stride + (int64_t)row * P.ld_dense + cbase;
-              const float sc = P.dense_scale;
-              if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                  *reinterpret_cast<float4*>(dst + i) =
-                      make_float4(__uint_as_float(v[i]) * sc, __uint_as_float(v[i + 1]) * sc,
-                                  __uint_as_float(v[i + 2]) * sc, __uint_as_float(v[i + 3]) * sc);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (i < nvalid) dst[i] = __uint_as_float(v[i]) * sc;
-              }
-            }
+            if (row_ok)
+              store_dense_chunk<false>(P.dense + (int64_t)ks * P.partial_stride + (int64_t)row * P.ld_dense + cbase, v, nvalid,
+                                       P.dense_scale);
           } else {   // MODE_COUNT
             if (ti >= 0) {
               const int64_t gbase = P.index_base + cbase;
@@ -593,7 +622,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
         tc_fence_before();
         __syncwarp();
 #ifdef FRX_TRACE
-        if (P.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && (t - t0) < 256) P.trace[(t - t0) * 4 + 3] = clock64();
+        if (P.trace && bid == 0 && ew == 0 && lane == 0 && (t - t0) < 256) P.trace[(t - t0) * 4 + 3] = clock64();
 #endif
         if (lane == 0) {
           if (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&tail->tmem_empty[as]), 0));   // the leader's barrier
@@ -624,10 +653,10 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
 
   // =========================== teardown ===========================
 #ifdef FRX_TRACE
-  if (P.cta_trace && threadIdx.x == EPI_WARP0 * 32) {
+  if (P.cta_trace && tid == EPI_WARP0 * 32) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    P.cta_trace[blockIdx.x * 4 + 3] = (long long)gt;
+    P.cta_trace[bid * 4 + 3] = (long long)gt;
   }
 #endif
   tc_fence_before();
@@ -639,7 +668,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
 }
 
 template <int MODE, bool TF32>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __maxnreg__(KERNEL_REGS)
 score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ ScoreParams P) {
   score_body<MODE, TF32, false>(tmap_a, tmap_b, P);
@@ -647,7 +676,7 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 
 // The same kernel on CTA pairs: clusters of two CTAs (the two SMs of a TPC), tcgen05 cta_group::2.
 template <int MODE, bool TF32>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(KERNEL_REGS)
 score_kernel_pair(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ ScoreParams P) {
   score_body<MODE, TF32, true>(tmap_a, tmap_b, P);
@@ -1291,12 +1320,14 @@ static int score_topk_impl(const void* a, int64_t ld_a, const void* b, int64_t l
     static const int refine_env = getenv("FRX_REFINE_EVERY") ? atoi(getenv("FRX_REFINE_EVERY")) : 0;   // tuning knob
     P.refine_every = refine_env >= 2 ? refine_env : REFINE_EVERY;
   }
+  if (dense_out) {   // the main pass writes the scores from the same accumulators (no second contraction)
+    FRX_CHECK_ARG(ld_dense >= n_posts, "frx_score_topk: ld_dense %lld below n_posts", (long long)ld_dense);
+    P.dense = dense_out;
+    P.ld_dense = ld_dense;
+  }
   rc = launch_score<MODE_TOPK, TF32>(a, ld_a, b, ld_b, nb, n_posts, d, plan, P, st);
   if (rc) return rc;
-  rc = run_merge(plan);
-  if (rc) return rc;
-  if (dense_out) return score_dense_impl<TF32>(a, ld_a, b, ld_b, nb, n_posts, d, dense_out, ld_dense, stream);
-  return FRX_OK;
+  return run_merge(plan);
 }
 
 // out[m, n] = scale * sum_k A[m, k] * B[n, k] on the tf32 tensor-core path (used by the 3xTF32 brand embedding).

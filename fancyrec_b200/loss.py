@@ -12,6 +12,7 @@ result (loss.py:85 vs :87-143), and `direction != 'all'` raises TypeError (loss.
 import torch
 import torch.nn as nn
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from . import ops
 from .util.constant import device
@@ -41,11 +42,15 @@ def euclidean_sim(im, s):
 class _LabFn(Function):
     @staticmethod
     def forward(ctx, brand_embs):
-        loss, d_brand = ops.lab_fwd_bwd(brand_embs, True)
-        ctx.save_for_backward(d_brand)
+        # the gradient tile / GEMM run only when autograd will ask for them (not under no_grad / validation)
+        want = ctx.needs_input_grad[0]
+        loss, d_brand = ops.lab_fwd_bwd(brand_embs, want)
+        if want:
+            ctx.save_for_backward(d_brand)
         return loss.reshape(())
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         d_brand, = ctx.saved_tensors
         return d_brand * grad_out
@@ -65,11 +70,14 @@ class LabLoss(nn.Module):
 class _TripletFn(Function):
     @staticmethod
     def forward(ctx, brand_ids, brand_emb, post_emb, margin, mean_style):
-        loss, d_brand, d_post = ops.triplet_fwd_bwd(brand_ids, brand_emb, post_emb, margin, mean_style, True)
-        ctx.save_for_backward(d_brand, d_post)
+        want = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]     # False under no_grad: forward kernels only
+        loss, d_brand, d_post = ops.triplet_fwd_bwd(brand_ids, brand_emb, post_emb, margin, mean_style, want)
+        if want:
+            ctx.save_for_backward(d_brand, d_post)
         return loss.reshape(())
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         d_brand, d_post = ctx.saved_tensors
         return None, d_brand * grad_out, d_post * grad_out, None, None

@@ -11,6 +11,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from . import ops
 from .util.constant import device
@@ -28,11 +29,14 @@ def cosine_sim(im, s):
 class _CrossCLRFn(Function):
     @staticmethod
     def forward(ctx, brand, post, temperature, negative_w, mean_style):
-        loss, d_brand, d_post = ops.crossclr_fwd_bwd(brand, post, temperature, negative_w, mean_style, True)
-        ctx.save_for_backward(d_brand, d_post)
+        want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]     # False under no_grad: forward kernels only
+        loss, d_brand, d_post = ops.crossclr_fwd_bwd(brand, post, temperature, negative_w, mean_style, want)
+        if want:
+            ctx.save_for_backward(d_brand, d_post)
         return loss.reshape(())
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         d_brand, d_post = ctx.saved_tensors
         return d_brand * grad_out, d_post * grad_out, None, None, None
@@ -63,12 +67,15 @@ class CrossCLR_onlyIntraModality(nn.Module):
 class _ContrastiveFn(Function):
     @staticmethod
     def forward(ctx, brand, post, keys, mask_col0, no_intra, temperature, negative_w, mean_style):
+        want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]     # False under no_grad: forward kernels only
         loss, d_brand, d_post = ops.contrastive_fwd_bwd(brand, post, keys, mask_col0, no_intra, temperature,
-                                                        negative_w, mean_style, True)
-        ctx.save_for_backward(d_brand, d_post)
+                                                        negative_w, mean_style, want)
+        if want:
+            ctx.save_for_backward(d_brand, d_post)
         return loss.reshape(())
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         d_brand, d_post = ctx.saved_tensors
         return d_brand * grad_out, d_post * grad_out, None, None, None, None, None, None

@@ -37,9 +37,10 @@ def round_up(v, m):
 
 # ---------------------------------------------------------------------------------------------
 def finalize_posts(visual, text=None, row_ptr=None, row_idx=None, visual_norm=False, text_norm=False,
-                   final_norm=True, want_f32=False, want_bf16=True):
+                   final_norm=True, want_f32=False, want_bf16=True, out_f32=None, out_bf16=None):
     """A1-A3 in one pass.  Returns (out_f32 | None, out_bf16 | None); out_bf16 is [NP, round_up(D, 64)]
-    with zero padding, the operand layout of score_*."""
+    with zero padding, the operand layout of score_*.  `out_f32` / `out_bf16`: write into these caller-owned
+    buffers (same shapes) instead of allocating."""
     lib = _lib.load()
     _req(visual, torch.float32, "visual", 2)
     dv = visual.shape[1]
@@ -58,9 +59,19 @@ def finalize_posts(visual, text=None, row_ptr=None, row_idx=None, visual_norm=Fa
             raise ValueError("text has %d rows, expected %d" % (text.shape[0], n_posts))
     d = dv + dt
     flags = (VISUAL_NORM if visual_norm else 0) | (TEXT_NORM if text_norm else 0) | (FINAL_NORM if final_norm else 0)
-    out_f32 = torch.empty((n_posts, d), dtype=torch.float32, device=visual.device) if want_f32 else None
     ld = round_up(d, 64)
-    out_bf16 = torch.empty((n_posts, ld), dtype=torch.bfloat16, device=visual.device) if want_bf16 else None
+    if out_f32 is not None:
+        _req(out_f32, torch.float32, "out_f32", 2)
+        if tuple(out_f32.shape) != (n_posts, d):
+            raise ValueError("out_f32 must be [%d, %d]" % (n_posts, d))
+    elif want_f32:
+        out_f32 = torch.empty((n_posts, d), dtype=torch.float32, device=visual.device)
+    if out_bf16 is not None:
+        _req(out_bf16, torch.bfloat16, "out_bf16", 2)
+        if tuple(out_bf16.shape) != (n_posts, ld):
+            raise ValueError("out_bf16 must be [%d, %d]" % (n_posts, ld))
+    elif want_bf16:
+        out_bf16 = torch.empty((n_posts, ld), dtype=torch.bfloat16, device=visual.device)
     with torch.cuda.device(visual.device):
         rc = lib.frx_finalize_posts(_ptr(visual), _ptr(row_ptr), _ptr(row_idx), _ptr(text), n_posts, dv, dt, flags,
                                     _ptr(out_f32), _ptr(out_bf16), ld, _stream(visual))

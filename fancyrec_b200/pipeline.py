@@ -1,0 +1,114 @@
+"""Pipelined evaluation of a stream of batches on one GPU (or one shard of a post-sharded job).
+
+`evaluator.test_post_ranking` is one synchronous pass: finalise the posts (HBM-bound), contract them against the brands
+with the fused top-k epilogue (tensor-bound), reduce the rank statistics, copy 40 KB to the host, aggregate in float64.
+Run back to back, that leaves the tensor cores idle during finalisation, the HBM pipe idle during the contraction and the
+whole GPU idle while the host aggregates.  When evaluations come as a stream -- validation every epoch
+(trainer.py:282-288), a sweep over checkpoints or test splits, the chunks of a post set larger than HBM -- this module
+keeps every unit busy:
+
+  * side stream   post finalisation of batch t+1.  The contraction kernel leaves room on every SM for exactly one
+                  finalise block (score.cu: KERNEL_REGS), so the two kernels are co-resident and the HBM-bound pass hides
+                  behind the tensor-bound one;
+  * main stream   brand side, fused score + top-k, rank statistics, pack, ASYNCHRONOUS copy of the packed block into
+                  pinned host memory of batch t;
+  * host          float64 aggregation (evaluator.py:129-143) of batch t-1 while the device works on t and t+1.
+
+Results are the same 8-tuples the synchronous call returns, bit for bit (tests/test_gpu_pipeline.py).
+"""
+import numpy as np
+import torch
+
+from . import ops, ranking, sharded
+
+
+class EvalPipeline:
+    def __init__(self, device, nb, n_posts_local, dv, dt=0, k=ranking.MIN_TOPK, n_posts_total=None, group=None,
+                 want_auc=False, overlap=True, depth=2, visual_norm=True, text_norm=True):
+        self.dev = torch.device(device)
+        self.nb, self.n_local, self.dv, self.dt, self.k = nb, n_posts_local, dv, dt, k
+        self.d = dv + dt
+        self.n_total = n_posts_local if n_posts_total is None else n_posts_total
+        self.group, self.want_auc, self.depth = group, want_auc, max(2, int(depth))
+        self.visual_norm, self.text_norm = visual_norm, text_norm
+        self.fin_stream = torch.cuda.Stream(self.dev) if overlap else None
+        ld = ops.round_up(self.d, 64)
+        rows = 6 if want_auc else 5
+        self.post_op = [torch.empty((n_posts_local, ld), dtype=torch.bfloat16, device=self.dev) for _ in range(self.depth)]
+        self.host = [torch.empty((rows, nb), dtype=torch.int64, pin_memory=True) for _ in range(self.depth)]
+        self.fin_done = [torch.cuda.Event() for _ in range(self.depth)]
+        self.op_free = [None] * self.depth          # recorded once the contraction that read post_op[slot] is enqueued
+        self.done = [torch.cuda.Event() for _ in range(self.depth)]
+        self.pending = [None] * self.depth          # ticket whose packed block sits (or will sit) in host[slot]
+        self.results = {}
+        self.workspace = None
+        self.ticket = 0
+        self.last_stats = None
+        self.last_brand_op = None
+
+    # -----------------------------------------------------------------------------------------
+    def submit(self, w, e, visual, text, labels_i32):
+        """Enqueue one evaluation: aspect tables w [NB+1, A] / e [A, D], post rows visual [NP, Dv] (+ text [NP, Dt]) and
+        labels [NP] int32, all on the device.  Returns a ticket for result(); never blocks on the device unless the
+        slot's previous result has not been collected yet (then it is collected first)."""
+        slot = self.ticket % self.depth
+        if self.pending[slot] is not None:
+            self._collect(slot)
+        cur = torch.cuda.current_stream(self.dev)
+        post_op = self.post_op[slot]
+        fin = self.fin_stream
+        if fin is not None:
+            inputs_ready = torch.cuda.Event()
+            inputs_ready.record(cur)
+            fin.wait_event(inputs_ready)                   # the caller produced visual / text on the current stream
+            if self.op_free[slot] is not None:
+                fin.wait_event(self.op_free[slot])         # the contraction that last read this operand buffer is over
+            with torch.cuda.stream(fin):
+                ops.finalize_posts(visual, text, visual_norm=self.visual_norm, text_norm=self.text_norm and text is not None,
+                                   final_norm=True, out_bf16=post_op)
+                self.fin_done[slot].record(fin)
+            for t in (visual, text):
+                if t is not None:
+                    t.record_stream(fin)
+        else:
+            ops.finalize_posts(visual, text, visual_norm=self.visual_norm, text_norm=self.text_norm and text is not None,
+                               final_norm=True, out_bf16=post_op)
+        brand = ops.brand_embed(w, e, nb=self.nb)
+        brand_op = ops.finalize_posts(brand, final_norm=True)[1]
+        if fin is not None:
+            cur.wait_event(self.fin_done[slot])
+        st = sharded.sharded_rank_statistics(brand_op, post_op, labels_i32, self.d, self.k, self.n_total, group=self.group,
+                                             workspace=self.workspace, want_auc=self.want_auc)
+        self.workspace = st["workspace"]
+        packed = ranking.pack_statistics(st, self.want_auc)
+        self.host[slot].copy_(packed, non_blocking=True)
+        self.done[slot].record(cur)
+        free = torch.cuda.Event()
+        free.record(cur)
+        self.op_free[slot] = free
+        self.last_stats, self.last_brand_op = st, brand_op
+        ticket = self.ticket
+        self.pending[slot] = ticket
+        self.ticket += 1
+        return ticket
+
+    def _collect(self, slot):
+        ticket = self.pending[slot]
+        self.done[slot].synchronize()
+        stats = ranking.unpack_statistics(self.host[slot].numpy(), self.n_total, self.want_auc)
+        self.results[ticket] = ranking.aggregate(stats, self.n_total, self.want_auc)
+        self.pending[slot] = None
+
+    def result(self, ticket):
+        """The 8-tuple (MedR, MeanR, AUC, NDCG@10, NDCG@50, r1, r5, r10) of a submitted batch (blocks until it is there)."""
+        if ticket not in self.results:
+            slot = ticket % self.depth
+            if self.pending[slot] != ticket:
+                raise KeyError("ticket %r is neither pending nor collected" % (ticket,))
+            self._collect(slot)
+        return self.results.pop(ticket)
+
+    def drain(self):
+        for slot in range(self.depth):
+            if self.pending[slot] is not None:
+                self._collect(slot)

@@ -11,7 +11,8 @@ from . import ops
 
 HIT_DEPTH = 50          # evaluator.py:120 reads NDCG@50 -> 50 relevance bits per brand
 MIN_TOPK = 64
-DENSE_BUDGET_BYTES = 2 << 30
+DENSE_BUDGET_BYTES = 2 << 30          # row-chunked AUC sweep: bytes of one dense score tile
+FUSED_DENSE_BUDGET_BYTES = 8 << 30    # AUC fast path: the fused top-k pass also writes the [NB, NP] fp32 scores when they fit
 
 
 # Score precision (north_star: 1e-3 relative for bf16 inputs, 1e-5 for tf32):
@@ -54,8 +55,11 @@ def device_rank_statistics(brand_bf16, post_bf16, labels_i32, d, k=MIN_TOPK, wan
     nb = brand_bf16.shape[0]
     dev = post_bf16.device
     k = max(int(k), min(MIN_TOPK, 1024))
+    # exact AUC needs every score once more (against the positives' scores, which this pass produces): when the matrix fits
+    # the budget the fused pass writes it from its own accumulators, else the sweep re-contracts row chunks (auc_sweep)
+    fused_dense = want_auc and dense_fits(nb, post_bf16.shape[0])
     res = ops.score_topk(brand_bf16, post_bf16, k, d=d, labels=labels_i32, index_base=index_base,
-                         workspace=workspace)
+                         workspace=workspace, dense=fused_dense)
     n_pos, best_score, best_index = ops.label_stats(labels_i32, res["pos_score"], nb, index_base)
     hit_mask, first_in_list = ops.rank_from_topk(res["index"], labels_i32, index_base)
     out = dict(topk_scores=res["scores"], topk_index=res["index"], n_pos=n_pos, best_score=best_score,
@@ -65,7 +69,7 @@ def device_rank_statistics(brand_bf16, post_bf16, labels_i32, d, k=MIN_TOPK, wan
     if want_auc:
         seg_ptr, pos_sorted = ops.group_positives(labels_i32, res["pos_score"], n_pos)
         out["auc_num"] = auc_sweep(ops, brand_bf16, post_bf16, d, labels_i32, seg_ptr, pos_sorted, best_score,
-                                   best_index, index_base, before_first)
+                                   best_index, index_base, before_first, dense=res.get("dense"))
     else:
         # enqueued unconditionally: frx_score_count skips every 128-brand tile without a missing first positive
         thr_index = ops.missing_thresholds(n_pos, first_in_list, best_index)
@@ -74,14 +78,24 @@ def device_rank_statistics(brand_bf16, post_bf16, labels_i32, d, k=MIN_TOPK, wan
     return out
 
 
+def dense_fits(nb, n_posts):
+    return 4 * nb * n_posts <= FUSED_DENSE_BUDGET_BYTES
+
+
 def auc_sweep(kernels, brand_op, post_op, d, labels_i32, seg_ptr, pos_sorted, best_score, best_index, index_base,
-              before_first):
+              before_first, dense=None):
     """Exact AUC numerators (evaluator.py:111-113) of the posts in `post_op` against the sorted positives in
-    (seg_ptr, pos_sorted) -- which may be the positives of the WHOLE job when `post_op` is one shard of it -- by
-    sweeping dense score tiles of at most DENSE_BUDGET_BYTES, never the whole matrix.  Also accumulates into
-    `before_first` the number of these posts that precede each brand's best positive.  Returns auc_num [NB] int64."""
+    (seg_ptr, pos_sorted) -- which may be the positives of the WHOLE job when `post_op` is one shard of it.
+    `dense` = the [NB, NP] scores the fused top-k pass wrote on its way: one streaming pass over them.  Without it
+    (matrix above FUSED_DENSE_BUDGET_BYTES) row chunks of at most DENSE_BUDGET_BYTES are re-contracted and swept, never
+    the whole matrix.  Also accumulates into `before_first` the number of these posts that precede each brand's best
+    positive.  Returns auc_num [NB] int64."""
     nb, n_posts = brand_op.shape[0], post_op.shape[0]
     auc_num = torch.zeros(nb, dtype=torch.int64, device=post_op.device)
+    if dense is not None:
+        kernels.auc_rows(dense, 0, labels_i32, seg_ptr, pos_sorted, best_score, best_index, auc_num, before_first,
+                         index_base)
+        return auc_num
     rows = max(1, min(nb, DENSE_BUDGET_BYTES // (4 * max(n_posts, 1))))
     if rows >= 128:
         rows = rows // 128 * 128
@@ -95,13 +109,16 @@ def auc_sweep(kernels, brand_op, post_op, d, labels_i32, seg_ptr, pos_sorted, be
     return auc_num
 
 
-def host_statistics(dev_stats, n_posts, want_auc=True, kernels=ops):
-    """Device statistics -> the integer per-brand arrays the metrics are functions of (NumPy, host).
-    Everything is packed by one kernel into one int64 [rows, NB] tensor so that the device->host read is ONE copy
-    (`kernels`: provider of the device steps, as in sharded.py)."""
-    packed = kernels.pack_rank_stats(dev_stats["n_pos"], dev_stats["first_in_list"], dev_stats["before_first"],
-                                 dev_stats["hit_mask"], dev_stats["auc_num"] if want_auc else None,
-                                 all_valid=want_auc).cpu().numpy()
+def pack_statistics(dev_stats, want_auc=True, kernels=ops):
+    """Everything the host needs, packed by one kernel into one int64 [5 | 6, NB] DEVICE tensor, so that the
+    device->host read of an evaluation is ONE copy (`kernels`: provider of the device steps, as in sharded.py)."""
+    return kernels.pack_rank_stats(dev_stats["n_pos"], dev_stats["first_in_list"], dev_stats["before_first"],
+                                   dev_stats["hit_mask"], dev_stats["auc_num"] if want_auc else None,
+                                   all_valid=want_auc)
+
+
+def unpack_statistics(packed, n_posts, want_auc=True):
+    """The packed block (NumPy, host) -> the integer per-brand arrays the metrics are functions of."""
     n_pos, first_in_list, before, valid, mask = packed[0], packed[1], packed[2], packed[3] != 0, packed[4]
     first_rank = np.where(valid, before, first_in_list)
     first_rank = np.where(n_pos > 0, first_rank, -1)
@@ -112,6 +129,11 @@ def host_statistics(dev_stats, n_posts, want_auc=True, kernels=ops):
     if want_auc:
         st["auc_num"] = packed[5].copy()
     return st
+
+
+def host_statistics(dev_stats, n_posts, want_auc=True, kernels=ops):
+    """Device statistics -> host integer arrays (blocking device->host copy; pipeline.py has the asynchronous form)."""
+    return unpack_statistics(pack_statistics(dev_stats, want_auc, kernels).cpu().numpy(), n_posts, want_auc)
 
 
 _IDEAL_CACHE = {}
@@ -170,6 +192,8 @@ def aggregate(stats, n_posts, want_auc=True):
     if want_auc:
         num = np.asarray(stats["auc_num"], dtype=np.int64)[has].astype(np.float64)
         den = (n_pos[has] * (n_posts - n_pos[has])).astype(np.float64)   # exact below 2^53, as float(int)/int is
+        if not den.all():        # a brand owns every post: float(num) / (len(pos) * 0), evaluator.py:117
+            raise ZeroDivisionError("float division by zero")
         auc = np.average(num / den)
     else:
         auc = np.float64("nan")

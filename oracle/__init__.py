@@ -14,5 +14,6 @@ Parity status: PINNED.  Every function here is checked (tests/test_oracle_*.py)
 against golden vectors produced by importing the reference itself in the build
 container (tests/golden/make_golden.py, run with /root/reference mounted) and
 against the doctest values in the reference's util/ndcg.py:15-27,54-65.
-The reference is pure Python, so there is no ``oracle/_ref`` binary to build.
+``oracle/_ref`` (git-ignored, built by ``oracle/build_ref.py`` where /root/reference exists) holds the reference's own
+hot-path modules byte-compiled to sourceless .pyc files: the unmodified reference, runnable on the GPU box's host cores.
 """

@@ -26,7 +26,7 @@ class OracleKernels:
     def _local(self, index_base, n):
         return self.scores_full[:, index_base:index_base + n]
 
-    def score_topk(self, brand_op, post_op, k, d=None, labels=None, index_base=0, workspace=None):
+    def score_topk(self, brand_op, post_op, k, d=None, labels=None, index_base=0, workspace=None, dense=False):
         s = self._local(index_base, post_op.shape[0])
         idx = oref.topk_indices(s, k)
         sc = np.take_along_axis(s, idx, 1)
