@@ -43,6 +43,7 @@ SIGNATURES = {
     "frx_last_error": (ctypes.c_char_p, []),
     "frx_device_check": (c_i32, [c_i32]),
     "frx_finalize_posts": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
+    "frx_finalize_posts_bounded": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp]),
     "frx_brand_embed_workspace_bytes": (c_sz, [c_i32, c_i32, c_i32]),
     "frx_brand_embed": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_sz, c_vp]),
     "frx_score_topk_workspace_bytes": (c_sz, [c_i32, c_i64, c_i32, c_i32]),
@@ -65,6 +66,7 @@ SIGNATURES = {
     "frx_pack_rank_stats": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "frx_group_positives": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "frx_auc_rows": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "frx_metric_scores": (c_i32, [c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "frx_triplet_workspace_bytes": (c_sz, [c_i32, c_i32]),
     "frx_triplet_fwd_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "frx_contrastive_workspace_bytes": (c_sz, [c_i32, c_i32, c_i32]),

@@ -719,7 +719,15 @@ extern "C" {
 int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_t* row_idx, const float* text,
                        int64_t n_posts, int dv, int dt, int flags, float* out_f32, uint16_t* out_bf16,
                        int64_t ld_bf16, void* stream) {
+  return frx_finalize_posts_bounded(visual, row_ptr, row_idx, text, n_posts, dv, dt, flags, out_f32, out_bf16, ld_bf16, 0,
+                                    stream);
+}
+
+int frx_finalize_posts_bounded(const float* visual, const int64_t* row_ptr, const int32_t* row_idx, const float* text,
+                               int64_t n_posts, int dv, int dt, int flags, float* out_f32, uint16_t* out_bf16,
+                               int64_t ld_bf16, int blocks_per_sm, void* stream) {
   using namespace frx;
+  FRX_CHECK_ARG(blocks_per_sm >= 0 && blocks_per_sm <= 32, "frx_finalize_posts: blocks_per_sm %d outside 0..32", blocks_per_sm);
   if (n_posts == 0) return FRX_OK;
   FRX_CHECK_ARG(visual != nullptr && dv > 0, "frx_finalize_posts: visual is NULL or dv <= 0");
   FRX_CHECK_ARG(n_posts >= 0 && dt >= 0, "frx_finalize_posts: negative size");
@@ -744,7 +752,7 @@ int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_
     // 5 per SM for the 2048-wide rows and the pooled rows.  Grid-stride loops cover the rest.
     const bool wide_unpooled = row_ptr == nullptr && d > 2048;
     int64_t blocks = n_posts;
-    const int64_t max_blocks = (int64_t)num_sms() * (wide_unpooled || d > 3072 ? 4 : 5);
+    const int64_t max_blocks = (int64_t)num_sms() * (blocks_per_sm > 0 ? blocks_per_sm : (wide_unpooled || d > 3072 ? 4 : 5));
     if (blocks > max_blocks) blocks = max_blocks;
     if (row_ptr != nullptr) {
       if (d <= 3072) finalize_block_kernel<3, true><<<(int)blocks, 256, 0, st>>>(P);

@@ -357,9 +357,138 @@ __global__ void reduce_shard_stats_kernel(const int32_t* __restrict__ n_pos_g, c
   }
 }
 
+// ---- A10: util/metric.py scorers (P@k, AP@k, RR, NDCG@k, DCG@k) over batches of sorted label lists ------------
+// One warp per list.  Integer label lists (graded relevance) in, float64 scores out, bit-identical to the reference's
+// Python arithmetic: every float64 operation is done in the reference's order by one lane, the warp's job is to find the
+// positions that matter (ballots over 32 labels at a time: zero-gain positions add +0.0 and are skipped) and the
+// descending order of the grades for the ideal DCG.  `log2_table[i]` = math.log(i, 2) computed on the HOST (CPython's
+// two-argument log is log(x) / log(2), which no device intrinsic reproduces bit for bit).
+enum { SCORER_P = 0, SCORER_AP = 1, SCORER_RR = 2, SCORER_NDCG = 3, SCORER_DCG = 4 };
+
+__device__ __forceinline__ int warp_max_i32(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+  return v;
+}
+
+// util/metric.py:80-88 (NDCGScorer.getDCG) over the first `length` labels, in list order
+__device__ double ndcg_dcg_in_order(const int32_t* lab, int length, const double* log2_table, int lane) {
+  double dcg = 0.0;
+  for (int base = 0; base < length; base += 32) {
+    const int i = base + lane;
+    const int g = i < length ? max(lab[i], 0) : 0;
+    uint32_t m = __ballot_sync(0xffffffffu, g > 0);
+    while (m) {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+      const int gl = __shfl_sync(0xffffffffu, g, l);
+      const int pos = base + l;
+      if (pos == 0) dcg = (double)gl;                                   // dcg = max(sorted_labels[0], 0)
+      else dcg += (double)gl / log2_table[pos + 1];                     // float(rel) / math.log(i + 1, 2)
+    }
+  }
+  return dcg;
+}
+
+__global__ void __launch_bounds__(256) scorer_kernel(const int32_t* __restrict__ labels, int64_t ld,
+                                                     const int32_t* __restrict__ lengths, int n_lists, int max_len, int kind,
+                                                     int k, const double* __restrict__ log2_table, double* __restrict__ out) {
+  const int list = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (list >= n_lists) return;
+  const int32_t* lab = labels + (int64_t)list * ld;
+  const int n = lengths ? min(max(lengths[list], 0), max_len) : max_len;
+  const int length = (k > 0 && k <= n) ? k : n;                         // MetricScorer.getLength
+  const double nan = __longlong_as_double(0x7FF8000000000000ll);
+  double res = 0.0;
+  if (kind == SCORER_P) {                                               // util/metric.py:58-68
+    int rel = 0;
+    for (int i = lane; i < length; i += 32) rel += lab[i] >= 1 ? 1 : 0;
+    rel = (int)__reduce_add_sync(0xffffffffu, (unsigned)rel);
+    res = length > 0 ? (double)rel / (double)length : nan;
+  } else if (kind == SCORER_RR) {                                       // util/metric.py:49-55 (whole list, not @k)
+    res = 0.0;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const uint32_t m = __ballot_sync(0xffffffffu, i < n && lab[i] >= 1);
+      if (m) { res = 1.0 / (double)(base + __ffs(m)); break; }
+    }
+  } else if (kind == SCORER_AP) {                                       // util/metric.py:26-45
+    int nr = 0;
+    for (int i = lane; i < n; i += 32) nr += lab[i] > 0 ? 1 : 0;
+    nr = (int)__reduce_add_sync(0xffffffffu, (unsigned)nr);
+    double ap = 0.0;
+    int rel = 0;
+    for (int base = 0; base < length && nr > 0; base += 32) {
+      const int i = base + lane;
+      uint32_t m = __ballot_sync(0xffffffffu, i < length && lab[i] >= 1);
+      while (m) {
+        const int l = __ffs(m) - 1;
+        m &= m - 1;
+        rel += 1;
+        ap += (double)rel / ((double)(base + l) + 1.0);
+      }
+    }
+    res = nr > 0 ? ap / (double)nr : 0.0;
+  } else if (kind == SCORER_NDCG) {                                     // util/metric.py:71-92
+    if (n == 0) res = nan;                                              // sorted_labels[0] raises IndexError there
+    else {
+      const double d = ndcg_dcg_in_order(lab, length, log2_table, lane);
+      // ideal: the same sum over sorted(labels, reverse=True)[:length]; only positive grades add anything, so walk the
+      // distinct positive grades in descending order (a handful) and emit each as many times as it occurs
+      double ideal = 0.0;
+      int pos = 0, bound = 0x7FFFFFFF;
+      while (pos < length) {
+        int g = 0, c = 0;
+        for (int i = lane; i < n; i += 32) { const int v = lab[i]; if (v < bound && v > g) g = v; }
+        g = warp_max_i32(g);
+        if (g <= 0) break;
+        for (int i = lane; i < n; i += 32) c += lab[i] == g ? 1 : 0;
+        c = (int)__reduce_add_sync(0xffffffffu, (unsigned)c);
+        for (int t = 0; t < c && pos < length; ++t, ++pos) {
+          if (pos == 0) ideal = (double)g; else ideal += (double)g / log2_table[pos + 1];
+        }
+        bound = g;
+      }
+      res = d / ideal;                                                  // 0 / 0 -> NaN: the reference raises ZeroDivisionError
+    }
+  } else {                                                              // SCORER_DCG, util/metric.py:95-116
+    // 0.01757 * sum(parts), parts over sorted_labels[:k]; CPython >= 3.12 sums floats with Neumaier compensation
+    const int cnt = k < n ? (k > 0 ? k : 0) : n;
+    double total = 0.0, comp = 0.0;
+    for (int i = 0; i < cnt; ++i) {
+      const double x = (ldexp(1.0, lab[i]) - 1.0) / log2_table[i + 2];  // (2**rel - 1) / math.log(index + 1, 2), index = i + 1
+      const double t = total + x;
+      if (fabs(total) >= fabs(x)) comp += (total - t) + x; else comp += (x - t) + total;
+      total = t;
+    }
+    if (comp != 0.0 && isfinite(comp)) total += comp;
+    res = 0.01757 * total;
+  }
+  if (lane == 0) out[list] = res;
+}
+
 }  // namespace frx
 
 extern "C" {
+
+int frx_metric_scores(const int32_t* labels, int64_t ld, const int32_t* lengths, int n_lists, int max_len, int kind, int k,
+                      const double* log2_table, double* out, void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(labels && log2_table && out, "frx_metric_scores: NULL pointer");
+  FRX_CHECK_ARG(n_lists > 0 && max_len >= 0 && ld >= max_len, "frx_metric_scores: bad sizes");
+  FRX_CHECK_ARG(kind >= SCORER_P && kind <= SCORER_DCG && k >= 0, "frx_metric_scores: unknown scorer %d / k %d", kind, k);
+  int dev = 0;
+  FRX_CUDA(cudaGetDevice(&dev));
+  const int rc = frx_device_check(dev);
+  if (rc) return rc;
+  const int warps_per_block = 8;
+  scorer_kernel<<<(n_lists + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, (cudaStream_t)stream>>>(
+      labels, ld, lengths, n_lists, max_len, kind, k, log2_table, out);
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
 
 int frx_reduce_shard_stats(const int32_t* n_pos_g, const float* best_score_g, const int32_t* best_index_g, int g, int nb,
                            int64_t stride_words, int32_t* n_pos, float* best_score, int32_t* best_index, void* stream) {

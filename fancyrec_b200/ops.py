@@ -37,10 +37,11 @@ def round_up(v, m):
 
 # ---------------------------------------------------------------------------------------------
 def finalize_posts(visual, text=None, row_ptr=None, row_idx=None, visual_norm=False, text_norm=False,
-                   final_norm=True, want_f32=False, want_bf16=True, out_f32=None, out_bf16=None):
+                   final_norm=True, want_f32=False, want_bf16=True, out_f32=None, out_bf16=None, blocks_per_sm=0):
     """A1-A3 in one pass.  Returns (out_f32 | None, out_bf16 | None); out_bf16 is [NP, round_up(D, 64)]
     with zero padding, the operand layout of score_*.  `out_f32` / `out_bf16`: write into these caller-owned
-    buffers (same shapes) instead of allocating."""
+    buffers (same shapes) instead of allocating.  `blocks_per_sm` bounds the resident blocks per SM (0 = the shape's
+    measured optimum; 1 = co-residency form for a launch that runs under a contraction, see pipeline.py)."""
     lib = _lib.load()
     _req(visual, torch.float32, "visual", 2)
     dv = visual.shape[1]
@@ -73,8 +74,8 @@ def finalize_posts(visual, text=None, row_ptr=None, row_idx=None, visual_norm=Fa
     elif want_bf16:
         out_bf16 = torch.empty((n_posts, ld), dtype=torch.bfloat16, device=visual.device)
     with torch.cuda.device(visual.device):
-        rc = lib.frx_finalize_posts(_ptr(visual), _ptr(row_ptr), _ptr(row_idx), _ptr(text), n_posts, dv, dt, flags,
-                                    _ptr(out_f32), _ptr(out_bf16), ld, _stream(visual))
+        rc = lib.frx_finalize_posts_bounded(_ptr(visual), _ptr(row_ptr), _ptr(row_idx), _ptr(text), n_posts, dv, dt, flags,
+                                            _ptr(out_f32), _ptr(out_bf16), ld, int(blocks_per_sm), _stream(visual))
     _lib.check(rc, "frx_finalize_posts")
     return out_f32, out_bf16
 
@@ -363,6 +364,35 @@ def auc_rows(scores, row0, labels, seg_ptr, pos_sorted, best_score, best_index, 
                               _ptr(pos_sorted), _ptr(best_score), _ptr(best_index), index_base, _ptr(auc_num),
                               _ptr(before_first), _stream(scores))
     _lib.check(rc, "frx_auc_rows")
+
+
+SCORER_KINDS = {"P": 0, "AP": 1, "RR": 2, "NDCG": 3, "DCG": 4}
+_LOG2_TABLES = {}
+
+
+def metric_scores(labels, kind, k=0, lengths=None):
+    """A10 on the device: util/metric.py's scorer `kind` ("P", "AP", "RR", "NDCG", "DCG") at cut-off k over a batch of
+    sorted label lists -- labels int32 [N, L] on the device, lengths [N] int32 (None: all L long) -> float64 [N],
+    bit-identical to getScorer("KIND@k").score(list) per list (NaN where the reference raises)."""
+    import math
+    lib = _lib.load()
+    _req(labels, torch.int32, "labels", 2)
+    n, length = labels.shape
+    if lengths is not None:
+        _req(lengths, torch.int32, "lengths", 1)
+    key = (labels.device, length)
+    table = _LOG2_TABLES.get(key)
+    if table is None:      # log2_table[i] = math.log(i, 2): the reference's own expression, evaluated on the host
+        table = torch.tensor([0.0] + [math.log(i, 2) for i in range(1, length + 2)], dtype=torch.float64).to(labels.device)
+        _LOG2_TABLES[key] = table
+    out = torch.empty(n, dtype=torch.float64, device=labels.device)
+    if n == 0:
+        return out
+    with torch.cuda.device(labels.device):
+        rc = lib.frx_metric_scores(_ptr(labels), labels.stride(0), _ptr(lengths), n, length, SCORER_KINDS[kind], int(k),
+                                   _ptr(table), _ptr(out), _stream(labels))
+    _lib.check(rc, "frx_metric_scores")
+    return out
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1,20 +1,23 @@
 """Pipelined evaluation of a stream of batches on one GPU (or one shard of a post-sharded job).
 
 `evaluator.test_post_ranking` is one synchronous pass: finalise the posts (HBM-bound), contract them against the brands
-with the fused top-k epilogue (tensor-bound), reduce the rank statistics, copy 40 KB to the host, aggregate in float64.
-Run back to back, that leaves the tensor cores idle during finalisation, the HBM pipe idle during the contraction and the
-whole GPU idle while the host aggregates.  When evaluations come as a stream -- validation every epoch
-(trainer.py:282-288), a sweep over checkpoints or test splits, the chunks of a post set larger than HBM -- this module
-keeps every unit busy:
+with the fused top-k epilogue (tensor-bound), reduce the rank statistics, copy 40 KB to the host, aggregate in float64
+-- and the GPU idles while the host copies and aggregates (0.6 ms of an 8 ms step at BASELINE.json's config 2).  When
+evaluations come as a stream -- validation every epoch (trainer.py:282-288), a sweep over checkpoints or test splits, the
+chunks of a post set larger than HBM -- this module keeps the device busy:
 
-  * side stream   post finalisation of batch t+1.  The contraction kernel leaves room on every SM for exactly one
-                  finalise block (score.cu: KERNEL_REGS), so the two kernels are co-resident and the HBM-bound pass hides
-                  behind the tensor-bound one;
-  * main stream   brand side, fused score + top-k, rank statistics, pack, ASYNCHRONOUS copy of the packed block into
-                  pinned host memory of batch t;
-  * host          float64 aggregation (evaluator.py:129-143) of batch t-1 while the device works on t and t+1.
+  * main stream   post finalisation, brand side, fused score + top-k, rank statistics, pack, ASYNCHRONOUS copy of the
+                  packed block into pinned host memory of batch t;
+  * host          float64 aggregation (evaluator.py:129-143) of batch t-1 while the device works on batch t.
 
-Results are the same 8-tuples the synchronous call returns, bit for bit (tests/test_gpu_pipeline.py).
+`overlap=True` additionally moves the finalisation of batch t+1 to a side stream so that it runs UNDER the contraction of
+batch t (the contraction kernel is built to leave room on every SM for one finalise block, score.cu: KERNEL_REGS, and
+the side-stream launch is bounded to one block per SM).  Measured on B200 (tools/gpu_overlap_probe.py):
+the two kernels do co-reside, but the contraction relies on the CTAs that share a post tile running in lock step so that
+their L2 reads coalesce; a co-resident streaming kernel breaks that, operand traffic hits the L2 slice throughput cap and
+BOTH kernels run 2-2.6x slower (makespan 11 ms instead of 7.1 ms back to back).  It is therefore off by default.
+
+Results are the same 8-tuples the synchronous call returns, bit for bit (tests/test_gpu_auc_pipeline.py).
 """
 import numpy as np
 import torch
@@ -24,7 +27,7 @@ from . import ops, ranking, sharded
 
 class EvalPipeline:
     def __init__(self, device, nb, n_posts_local, dv, dt=0, k=ranking.MIN_TOPK, n_posts_total=None, group=None,
-                 want_auc=False, overlap=True, depth=2, visual_norm=True, text_norm=True):
+                 want_auc=False, overlap=False, depth=2, visual_norm=True, text_norm=True):
         self.dev = torch.device(device)
         self.nb, self.n_local, self.dv, self.dt, self.k = nb, n_posts_local, dv, dt, k
         self.d = dv + dt
@@ -32,6 +35,7 @@ class EvalPipeline:
         self.group, self.want_auc, self.depth = group, want_auc, max(2, int(depth))
         self.visual_norm, self.text_norm = visual_norm, text_norm
         self.fin_stream = torch.cuda.Stream(self.dev) if overlap else None
+        self.side_blocks_per_sm = 1
         ld = ops.round_up(self.d, 64)
         rows = 6 if want_auc else 5
         self.post_op = [torch.empty((n_posts_local, ld), dtype=torch.bfloat16, device=self.dev) for _ in range(self.depth)]
@@ -64,8 +68,9 @@ class EvalPipeline:
             if self.op_free[slot] is not None:
                 fin.wait_event(self.op_free[slot])         # the contraction that last read this operand buffer is over
             with torch.cuda.stream(fin):
+                # one block per SM: what fits next to a resident contraction CTA (more would lock the contraction out)
                 ops.finalize_posts(visual, text, visual_norm=self.visual_norm, text_norm=self.text_norm and text is not None,
-                                   final_norm=True, out_bf16=post_op)
+                                   final_norm=True, out_bf16=post_op, blocks_per_sm=self.side_blocks_per_sm)
                 self.fin_done[slot].record(fin)
             for t in (visual, text):
                 if t is not None:

@@ -1,7 +1,8 @@
 """Rank-metric scorers with the reference's names and semantics (util/metric.py:6-123).
 
-Pure host code over one sorted label list; nothing in the reference calls it, the API is kept
-because north_star names it.
+`score(sorted_labels)` is the reference's host arithmetic over ONE list (nothing in the reference calls it; the API is
+kept because north_star names it).  `score_device(labels)` evaluates the same scorer over a BATCH of integer label
+lists on the GPU -- one warp per list, frx_metric_scores -- and returns float64 values bit-identical to `score`.
 """
 import math
 import random
@@ -22,8 +23,25 @@ class MetricScorer:
         base = type(self).__name__.replace("Scorer", "")
         return "%s@%d" % (base, self.k) if self.k > 0 else base
 
+    _KIND = None
+
+    def score_device(self, labels, lengths=None):
+        """Batch form on the device: labels int32 CUDA tensor [N, L] of sorted label lists (lengths [N] int32 for ragged
+        lists) -> float64 CUDA tensor [N], entry i == self.score(list i) bit for bit.  Raises what `score` raises
+        (ZeroDivisionError for an NDCG list without a positive grade or an empty P@k list)."""
+        if self._KIND is None:
+            import torch
+            return torch.zeros(labels.shape[0], dtype=torch.float64, device=labels.device)     # MetricScorer.score -> 0.0
+        from .. import ops
+        out = ops.metric_scores(labels, self._KIND, self.k, lengths)
+        if self._KIND in ("NDCG", "P") and bool((out != out).any()):
+            raise ZeroDivisionError("float division by zero")
+        return out
+
 
 class APScorer(MetricScorer):
+    _KIND = "AP"
+
     def __init__(self, k):
         MetricScorer.__init__(self, k)
 
@@ -40,6 +58,8 @@ class APScorer(MetricScorer):
 
 
 class RRScorer(MetricScorer):
+    _KIND = "RR"
+
     def score(self, sorted_labels):
         for pos, lab in enumerate(sorted_labels):
             if lab >= 1:
@@ -48,12 +68,16 @@ class RRScorer(MetricScorer):
 
 
 class PrecisionScorer(MetricScorer):
+    _KIND = "P"
+
     def score(self, sorted_labels):
         n = self.getLength(sorted_labels)
         return float(sum(1 for lab in sorted_labels[:n] if lab >= 1)) / n
 
 
 class NDCGScorer(PrecisionScorer):
+    _KIND = "NDCG"
+
     def score(self, sorted_labels):
         # no zero guard, as in the reference: all-zero labels raise ZeroDivisionError
         return self.getDCG(sorted_labels) / self.getIdealDCG(sorted_labels)
@@ -69,6 +93,8 @@ class NDCGScorer(PrecisionScorer):
 
 
 class DCGScorer(PrecisionScorer):
+    _KIND = "DCG"
+
     def score(self, sorted_labels):
         return self.getDCG(sorted_labels)
 

@@ -72,6 +72,13 @@ int         frx_device_check(int ordinal);
 int frx_finalize_posts(const float* visual, const int64_t* row_ptr, const int32_t* row_idx,
                        const float* text, int64_t n_posts, int dv, int dt, int flags,
                        float* out_f32, uint16_t* out_bf16, int64_t ld_bf16, void* stream);
+/* Same pass with a bound on the thread blocks the kernel keeps resident per SM (0 = the measured optimum of the shape,
+ * what frx_finalize_posts uses).  blocks_per_sm = 1 is the co-residency form: the contraction kernel (frx_score_*)
+ * leaves room on every SM for exactly ONE finalise block, so a finalisation launched on a second stream with this bound
+ * runs UNDER a contraction instead of queueing behind it or locking it out (fancyrec_b200/pipeline.py). */
+int frx_finalize_posts_bounded(const float* visual, const int64_t* row_ptr, const int32_t* row_idx,
+                               const float* text, int64_t n_posts, int dv, int dt, int flags,
+                               float* out_f32, uint16_t* out_bf16, int64_t ld_bf16, int blocks_per_sm, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * A4  brand embedding without the [NB, A, D] intermediate.
@@ -213,6 +220,17 @@ int frx_missing_thresholds(const int32_t* n_pos, const int32_t* first_in_list, c
 int frx_pack_rank_stats(const int32_t* n_pos, const int32_t* first_in_list, const unsigned long long* before_first,
                         const unsigned long long* hit_mask, const unsigned long long* auc_num, int nb, int all_valid,
                         long long* out, void* stream);
+
+/* frx_metric_scores (A10; util/metric.py:6-123): the reference's rank-metric scorers over a BATCH of sorted label lists,
+ * one warp per list.  labels int32 [n_lists, ld] (graded relevance, list i occupies labels[i*ld .. i*ld + lengths[i]);
+ * lengths NULL = every list has max_len entries).  kind: 0 P@k (PrecisionScorer), 1 AP@k (APScorer), 2 RR (RRScorer),
+ * 3 NDCG@k (NDCGScorer), 4 DCG@k (DCGScorer); k = 0 means "whole list" exactly as MetricScorer.getLength does.
+ * log2_table [max_len + 2] float64 with log2_table[i] = math.log(i, 2) for i >= 1, computed by the caller on the host
+ * (CPython evaluates log(i) / log(2); the table makes the device result bit-identical).  out float64 [n_lists]:
+ * bit for bit what `getScorer(name).score(list)` returns; where the reference raises (NDCG of an all-zero list:
+ * ZeroDivisionError; empty list) the entry is NaN and the Python mirror raises the same exception. */
+int frx_metric_scores(const int32_t* labels, int64_t ld, const int32_t* lengths, int n_lists, int max_len, int kind, int k,
+                      const double* log2_table, double* out, void* stream);
 
 /* frx_auc_rows: exact AUC numerators from dense score rows (evaluator.py:111-113):
  *   auc_num[row0 + r] += sum over positives e of brand (row0+r) of #{negatives el : e > el}
