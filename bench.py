@@ -735,8 +735,22 @@ def cpu_baseline(nb, sample_posts, cfg, steps=1, warmup=0):
 
 def reference_c1():
     """BASELINE.json configs[0] on the UNMODIFIED reference (oracle/_ref: the reference's own evaluator.test_post_ranking
-    and BrandAspects, byte-compiled from /root/reference by oracle/build_ref.py), gpu = -1 i.e. host cores:
-    50 brands x 10 000 posts, 2048-d + 1024-d rows, A = 2000, full 8-tuple incl. AUC."""
+    and BrandAspects, byte-compiled from /root/reference by oracle/build_ref.py) in its documented CPU mode gpu = -1,
+    i.e. a child process with CUDA_VISIBLE_DEVICES=-1 (README.md:64, bin/instance.sh:29-30): 50 brands x 10 000 posts,
+    2048-d + 1024-d rows, A = 2000, full 8-tuple incl. AUC."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="-1")
+    try:
+        p = subprocess.run([sys.executable, "-c", "import json, bench; print('C1JSON' + json.dumps(bench._reference_c1_inproc()))"],
+                           cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        for line in p.stdout.splitlines():
+            if line.startswith("C1JSON"):
+                return json.loads(line[6:])
+        return {"kind": "reference", "unavailable": (p.stderr or p.stdout)[-200:]}
+    except Exception as ex:  # noqa: BLE001
+        return {"kind": "reference", "unavailable": str(ex)[:200]}
+
+
+def _reference_c1_inproc():
     try:
         from oracle import build_ref
         ref = build_ref.load()

@@ -1,6 +1,7 @@
 // A6-A9: integer rank statistics behind AUC / NDCG@k / recall@k / MedR (evaluator.py:103-143,
 // util/ndcg.py).  Everything here is HBM/latency-bound integer work on warp-level primitives; the
 // float64 metric values are computed from these integers on the host exactly as the reference does.
+#include <type_traits>
 #include "common.cuh"
 
 namespace frx {
@@ -241,47 +242,73 @@ __global__ void __launch_bounds__(256) auc_rows_kernel(const float* __restrict__
       }
     }
     __syncthreads();
-    // 8 independent (score, label) loads in flight per thread: the sweep is latency-bound otherwise
+    // 8 independent (score, label) loads and 8 independent table lookups in flight per thread, then a branch-free
+    // resolve.  No range tests are needed: a score below every positive lands (clamped) in bucket 0, whose first
+    // positive is lo > s, so it counts 0; a score at or above every positive lands in the last bucket and passes all of
+    // its positives, so it counts m.  Only a NaN score needs care (`e > NaN` is False: it must add nothing).
     constexpr int U = 8;
-    unsigned int auc32 = 0, before32 = 0;      // per-batch partials stay 32-bit; folded into u64 per batch
-    for (int64_t j0 = c0 + threadIdx.x; j0 < c1; j0 += (int64_t)U * blockDim.x) {
+    const float* rowp = row + c0;
+    const int32_t* labp = labels + c0;
+    const int len = (int)(c1 - c0);                          // < 2^31: the caller checks that global indices fit int32
+    const int gbase = (int)(index_base + c0);
+    const bool first_chunk = ch == 0;
+    auto batch = [&](int j0, auto checked) {
+      constexpr bool CHECK = decltype(checked)::value;       // last, partial batch of the thread: bounds-checked loads
       float sv[U];
       int lv[U];
+      uint32_t tv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int64_t j = j0 + (int64_t)u * blockDim.x;
-        sv[u] = j < c1 ? __ldcs(row + j) : 0.f;            // streamed once: evict first, the labels stay in L2
-        lv[u] = j < c1 ? __ldg(labels + j) : b;            // out of range: treated as a positive -> skipped
+        const int j = j0 + u * 256;
+        const bool ok = !CHECK || j < len;
+        sv[u] = ok ? __ldcs(rowp + j) : __int_as_float(0x7FC00000);   // streamed once: evict first, labels stay in L2
+        lv[u] = ok ? __ldg(labp + j) : b;                    // out of range: NaN score, the brand's own label -> adds nothing
       }
-      const int g0idx = (int)(index_base + j0);            // global post index of sv[0]; fits int32 (checked by the caller)
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const bool in_range = j0 + (int64_t)u * blockDim.x < c1;
+        const int q = auc_bucket(sv[u], lo_s, inv_w);        // (int)NaN = 0, below lo -> negative: clamped to bucket 0
+        tv[u] = table[q > 0 ? q : 0];
+      }
+      unsigned int auc32 = 0, before32 = 0;                  // <= 8 * 4000 per batch: no 32-bit overflow
+      uint32_t slow = 0;                                     // slots whose bucket holds SEVERAL positives (rare)
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
         const float s = sv[u];
-        if (ch == 0 && in_range)
-          before32 += ((s > bs) || (s == bs && (g0idx + u * (int)blockDim.x) < bi)) ? 1u : 0u;
-        if (lv[u] == b) continue;              // negatives only (evaluator.py:112)
-        // idx = #{positives of this chunk <= s}; the negative adds m - idx
-        int idx;
-        if (!(s < hi_s)) idx = m;                           // at or above every positive; NaN: `e > NaN` is False for every e
-        else if (s < lo_s) idx = 0;                         // below every positive
-        else {
-          const uint32_t t = table[auc_bucket(s, lo_s, inv_w)];
-          idx = (int)(t & 0xFFFFu);
-          int n = (int)(t >> 16);
-          if (n <= kAucLinear) {
-            while (n > 0 && spos[idx] <= s) { ++idx; --n; }
-          } else {                             // crowded bucket (ties / clustered positives): binary search inside it
-            int lo = idx, hi = idx + n;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (spos[mid] > s) hi = mid; else lo = mid + 1; }
-            idx = lo;
-          }
+        if (first_chunk) {
+          before32 += s > bs ? 1u : 0u;
+          if (s == bs) before32 += (gbase + j0 + u * 256) < bi ? 1u : 0u;      // ties with the best positive: rare
         }
-        auc32 += (unsigned int)(m - idx);
+        // idx = #{positives of this chunk <= s} = table count + one compare against the bucket's first positive
+        // (spos[m] = +inf pads the end); a negative adds m - idx
+        const int first = (int)(tv[u] & 0xFFFFu);
+        const int n = (int)(tv[u] >> 16);
+        const int idx = first + ((n != 0 && spos[first] <= s) ? 1 : 0);
+        slow |= n > 1 ? (1u << u) : 0u;
+        auc32 += (lv[u] != b && s == s) ? (unsigned int)(m - idx) : 0u;        // negatives only (evaluator.py:112)
       }
-      auc += auc32; before += before32;          // <= 8 * 4096 per batch: no 32-bit overflow
-      auc32 = 0; before32 = 0;
-    }
+      while (slow) {                                         // redo these slots exactly: walk / search inside the bucket
+        const int u = __ffs(slow) - 1;
+        slow &= slow - 1;
+        float s = sv[0]; int l = lv[0]; uint32_t t = tv[0];
+#pragma unroll
+        for (int i = 1; i < U; ++i) { s = i == u ? sv[i] : s; l = i == u ? lv[i] : l; t = i == u ? tv[i] : t; }
+        const int first = (int)(t & 0xFFFFu);
+        int n = (int)(t >> 16), idx = first;
+        if (n <= kAucLinear) {
+          while (n > 0 && spos[idx] <= s) { ++idx; --n; }
+        } else {                                             // crowded bucket (ties / clustered positives): binary search
+          int lo = first, hi = first + n;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (spos[mid] > s) hi = mid; else lo = mid + 1; }
+          idx = lo;
+        }
+        const int quick = first + (spos[first] <= s ? 1 : 0);        // what the branch-free pass counted for this slot
+        if (l != b && s == s) auc32 -= (unsigned int)(idx - quick);   // m - idx instead of m - quick (idx >= quick)
+      }
+      auc += auc32; before += before32;
+    };
+    int j0 = threadIdx.x;
+    for (; j0 + (U - 1) * 256 < len; j0 += U * 256) batch(j0, std::false_type{});
+    if (j0 < len) batch(j0, std::true_type{});
   }
   // block reduce
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

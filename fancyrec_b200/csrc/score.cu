@@ -103,7 +103,9 @@ struct SmemTail {
   uint64_t full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
-  uint32_t hist[NUM_EPI_WARPS][256];
+  // per epilogue warp: 256-bin radix histogram of the select (first 1 KB), or the 32 x 16 fp32 transpose stage of the
+  // dense store (all 2 KB) -- never live at the same time
+  alignas(16) uint32_t scratch[NUM_EPI_WARPS][512];
   uint8_t tile_need[MAX_NEED_TILES];   // COUNT: m-tile has at least one row with a threshold (others are skipped)
 };
 constexpr size_t SMEM_BYTES = 1024 /* alignment slack */ + (size_t)RING_BYTES + sizeof(SmemTail);
@@ -273,6 +275,39 @@ __device__ __forceinline__ void store_dense_chunk(float* dst, const uint32_t (&v
   }
 }
 
+// The same chunk for the warp's 32 rows at once, transposed through shared memory so that every store instruction writes
+// 8 rows x 64 contiguous bytes (two whole sectors per row) instead of 32 rows x 16 bytes: a quarter of the LSU wavefronts
+// and no partially written sectors.  Lane r enters with its row's 32 columns in v; `stage` = 512 floats of this warp.
+// Layout of one half chunk (16 columns): row r at stage[16 r ..], its four float4 groups XOR-swizzled by (r >> 1) & 3 --
+// conflict-free both for the row-wise writes and for the reads (8 lanes cover rows 2j, 2j+1 completely).
+// Requires: all 32 lanes, 32 valid columns, 16-byte aligned row segments (base and ld).
+template <bool STREAM>
+__device__ __forceinline__ void store_dense_chunk_staged(float* base, int64_t ld, const uint32_t (&v)[32], float sc,
+                                                         float* stage, int lane, int rows_valid) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int phys = g ^ ((lane >> 1) & 3);
+      *reinterpret_cast<float4*>(stage + lane * 16 + 4 * phys) =
+          make_float4(__uint_as_float(v[half * 16 + 4 * g]) * sc, __uint_as_float(v[half * 16 + 4 * g + 1]) * sc,
+                      __uint_as_float(v[half * 16 + 4 * g + 2]) * sc, __uint_as_float(v[half * 16 + 4 * g + 3]) * sc);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = 8 * i + (lane >> 2), g = lane & 3;
+      const float4 o = *reinterpret_cast<const float4*>(stage + r * 16 + 4 * (g ^ ((r >> 1) & 3)));
+      if (r < rows_valid) {
+        float* dst = base + (int64_t)r * ld + half * 16 + 4 * g;
+        if (STREAM) __stcs(reinterpret_cast<float4*>(dst), o);
+        else *reinterpret_cast<float4*>(dst) = o;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int MODE, bool TF32, bool PAIR>
 __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ScoreParams& P) {
   using R = Ring<PAIR>;
@@ -438,7 +473,8 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
     const int ew = warp - EPI_WARP0;
     const int row_in_tile = q * 32 + lane;
     constexpr int CHUNKS = BN / 2 / 32;              // 4 chunks of 32 columns per warp per tile
-    uint32_t* hist = tail->hist[ew];
+    uint32_t* hist = tail->scratch[ew];
+    float* stage = reinterpret_cast<float*>(tail->scratch[ew]);
     int as = 0; uint32_t aphase = 0;
 #ifdef FRX_TRACE
     if (P.cta_trace && ew == 0 && lane == 0) {
@@ -457,6 +493,10 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
       const int64_t t0 = P.num_n_tiles * split / P.splits, t1 = P.num_n_tiles * (split + 1) / P.splits;
       const int row = m_tile * BM + row_in_tile;
       const bool row_ok = row < P.nb;
+      // dense output: rows of this warp inside the matrix, and whether 16-byte vector stores of row segments are aligned
+      const int warp_rows = min(max(P.nb - (m_tile * BM + q * 32), 0), 32);
+      const bool dense_vec_ok = P.dense != nullptr && (P.ld_dense & 3) == 0 && (P.partial_stride & 3) == 0 &&
+                                (reinterpret_cast<uintptr_t>(P.dense) & 15) == 0;
 
       // per-row state
       float thr = row_ok ? -INFINITY : INFINITY;     // TOPK: append threshold
@@ -526,8 +566,13 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
 
           if (MODE == MODE_TOPK) {
             // the caller also wants the score matrix (exact-AUC sweep): same accumulators, written on the way
-            if (P.dense != nullptr && row_ok)
-              store_dense_chunk<true>(P.dense + (int64_t)row * P.ld_dense + cbase, v, nvalid, 1.0f);
+            if (P.dense != nullptr) {
+              float* wbase = P.dense + (int64_t)(m_tile * BM + q * 32) * P.ld_dense + cbase;
+              if (nvalid == 32 && dense_vec_ok)
+                store_dense_chunk_staged<true>(wbase, P.ld_dense, v, 1.0f, stage, lane, warp_rows);
+              else if (row_ok)
+                store_dense_chunk<true>(wbase + (int64_t)lane * P.ld_dense, v, nvalid, 1.0f);
+            }
             if (nvalid < 32) {                       // last tile only: out-of-range columns can never qualify
 #pragma unroll
               for (int i = 0; i < 32; ++i) if (i >= nvalid) v[i] = 0x7FC00000u;   // NaN: fails every >=
@@ -601,9 +646,11 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
               }
             }
           } else if (MODE == MODE_DENSE) {
-            if (row_ok)
-              store_dense_chunk<false>(P.dense + (int64_t)ks * P.partial_stride + (int64_t)row * P.ld_dense + cbase, v, nvalid,
-                                       P.dense_scale);
+            float* wbase = P.dense + (int64_t)ks * P.partial_stride + (int64_t)(m_tile * BM + q * 32) * P.ld_dense + cbase;
+            if (nvalid == 32 && dense_vec_ok)
+              store_dense_chunk_staged<false>(wbase, P.ld_dense, v, P.dense_scale, stage, lane, warp_rows);
+            else if (row_ok)
+              store_dense_chunk<false>(wbase + (int64_t)lane * P.ld_dense, v, nvalid, P.dense_scale);
           } else {   // MODE_COUNT
             if (ti >= 0) {
               const int64_t gbase = P.index_base + cbase;

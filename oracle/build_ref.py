@@ -1,13 +1,14 @@
 """Recipe for oracle/_ref (TEST / BENCH INFRASTRUCTURE ONLY -- never imported by fancyrec_b200/).
 
 The reference is pure Python, so "building" it means byte-compiling the modules of the hot path from the sources
-where they lie under /root/reference into oracle/_ref/*.pyc (sourceless imports).  No reference source is copied into
+where they lie under /root/reference into oracle/_ref/*.ref (CPython code objects in .pyc format; the extension is
+ours because snapshot tools tend to drop *.pyc).  No reference source is copied into
 this repository: oracle/_ref/ is git-ignored, holds only compiled code objects, and travels to the GPU box like our own
 built libfrx_b200.so.  There it lets bench.py time the UNMODIFIED reference (`evaluator.test_post_ranking`,
 evaluator.py:85-143, with the reference's own BrandAspects, model.py:406-428) on the box's host cores, and lets the
 tests cross-check the oracle port against it.
 
-    python oracle/build_ref.py            # -> oracle/_ref/{evaluator,model,loss,loss_ctrs}.pyc, oracle/_ref/util/*.pyc
+    python oracle/build_ref.py            # -> oracle/_ref/{evaluator,model,loss,loss_ctrs}.ref, oracle/_ref/util/*.ref
 """
 import os
 import py_compile
@@ -28,7 +29,7 @@ def build(verbose=False):
         return False
     for rel in MODULES:
         src = os.path.join(REF_SRC, rel)
-        dst = os.path.join(OUT, rel + "c")             # sourceless layout: <module>.pyc next to where <module>.py would be
+        dst = os.path.join(OUT, rel[:-3] + ".ref")     # <module>.ref where <module>.py would be, loaded by _RefFinder
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         py_compile.compile(src, cfile=dst, dfile="reference/" + rel, doraise=True, optimize=0,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
@@ -57,10 +58,11 @@ def load():
     import numpy as np
     if not hasattr(np, "asfarray"):
         np.asfarray = lambda a, dtype=np.float64: np.asarray(a, dtype=dtype)
-    saved_path, saved_mods = list(sys.path), {k: v for k, v in sys.modules.items() if k == "util" or k.startswith("util.")}
+    saved_mods = {k: v for k, v in sys.modules.items() if k == "util" or k.startswith("util.")}
     for k in saved_mods:
         del sys.modules[k]
-    sys.path.insert(0, OUT)
+    finder = _RefFinder()
+    sys.meta_path.insert(0, finder)
     try:
         ns = types.SimpleNamespace()
         ns.evaluator = importlib.import_module("evaluator")
@@ -70,8 +72,28 @@ def load():
         ns.ndcg = importlib.import_module("util.ndcg")
         ns.metric = importlib.import_module("util.metric")
     finally:
-        sys.path[:] = saved_path
+        sys.meta_path.remove(finder)
     return ns
+
+
+class _RefFinder:
+    """Meta-path finder for the byte-compiled reference modules (top-level names evaluator / model / loss / loss_ctrs and
+    the package util.*), active only while load() imports them."""
+
+    def find_spec(self, name, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        rel = name.replace(".", os.sep)
+        pkg = os.path.join(OUT, rel, "__init__.ref")
+        mod = os.path.join(OUT, rel + ".ref")
+        if os.path.exists(pkg):
+            loader = importlib.machinery.SourcelessFileLoader(name, pkg)
+            return importlib.util.spec_from_file_location(name, pkg, loader=loader,
+                                                          submodule_search_locations=[os.path.join(OUT, rel)])
+        if os.path.exists(mod):
+            loader = importlib.machinery.SourcelessFileLoader(name, mod)
+            return importlib.util.spec_from_file_location(name, mod, loader=loader)
+        return None
 
 
 if __name__ == "__main__":
