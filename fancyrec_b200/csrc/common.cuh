@@ -46,6 +46,22 @@ int num_sms();
 int dense_tf32_scaled(const float* a, int64_t ld_a, const float* b, int64_t ld_b, int m, int64_t n, int k, float* out,
                       int64_t ld_out, float scale, void* stream, void* ksplit_ws = nullptr, size_t ksplit_ws_bytes = 0);
 
+// gemm3x.cu: fp32-grade GEMM on the tf32 tensor cores, 3xTF32 operand split inside the kernel (no split / transposed
+// copies in HBM).  C[m, n] = act(alpha * (sum_k A(m,k) B(n,k)) * col_scale[n] + col_shift[n]); an operand X is K-major
+// (x[row * ld + k]) or MN-major (x[k * ld + row]).
+struct Gemm3xDesc {
+  const float* a; int64_t lda; int a_mn;
+  const float* b; int64_t ldb; int b_mn;
+  float* c; int64_t ldc;
+  int m, n, k;
+  float alpha; const float* col_scale; const float* col_shift; int relu;
+};
+bool gemm3x_supported(const Gemm3xDesc& d);
+int gemm3x_plan_ksplit(const Gemm3xDesc* d, int count);                       // K split that fills the SMs (1 = none)
+size_t gemm3x_partial_floats(const Gemm3xDesc* d, int count, int ksplit);      // floats of the [ksplit][m][n] partial tiles
+int gemm3x_launch(cudaStream_t st, const Gemm3xDesc* d, int count, int ksplit, bool keep_partials, float* partial,
+                  size_t partial_floats);
+
 // finalize.cu: 3xTF32 operand preparation.  pattern 0 = [hi | lo | hi] (A side), 1 = [hi | hi | lo] (B side).
 void launch_split_rows(const float* x, const int64_t* ids, int rows, int cols, int64_t ld_x, float scale, int pattern,
                        float* out, cudaStream_t st);

@@ -4,7 +4,11 @@
 // launches (loss.py:91-93), the four sorts (loss.py:96-105) or the B^2 host loop (loss.py:116-119) of
 // the reference.  The GEMMs (tile, dS.brand, dS^T.post, softmax logits) run on the tensor cores as 3xTF32
 // (fp32-grade) through the same tcgen05 kernel as the scoring path; small fused row kernels do the rest.
+#include <cooperative_groups.h>
+#include <stdlib.h>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace frx {
 
@@ -173,6 +177,107 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     for (int w = 0; w < 8; ++w) t += red[w];
     out[0] = (float)(t * (double)scale);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TripletLoss, everything between the tile GEMM and the gradient GEMMs in ONE cooperative launch (block i = row i):
+//   phase 1  S[i,:] = sum over the K-split partial tiles of the tile GEMM, in split order (kept in shared memory and
+//            written once to global memory for the column reads of the other blocks)
+//   phase 2  rank of the diagonal in row i and in column i by counting (loss.py:96-105)  -> rank_p, rank_b, diag
+//   phase 3  hinge, same-brand mask, column-broadcast weights (loss.py:107-132) -> dS[i,:], the row's loss
+//   phase 4  block 0 adds the row losses in a fixed order (float64)
+// Replaces reduce_ksplit + tile_rank + triplet_row + reduce_partials (4 launches, S read back from HBM three times).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) triplet_tile_kernel(const float* __restrict__ partial, int ksplit, int b,
+                                                           const int64_t* __restrict__ ids, float margin, float scale,
+                                                           float* __restrict__ s, float* __restrict__ rank_p,
+                                                           float* __restrict__ rank_b, float* __restrict__ diag,
+                                                           float* __restrict__ ds, float* __restrict__ row_loss,
+                                                           float* __restrict__ loss_out) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ float srow[];                 // S[i, 0..b)
+  __shared__ float redf[8];
+  __shared__ int redi[8];
+  __shared__ double redd[8];
+  const int i = blockIdx.x;
+  const int64_t bb = (int64_t)b * b;
+  for (int j = threadIdx.x; j < b; j += blockDim.x) {
+    float acc = 0.f;
+    for (int ks = 0; ks < ksplit; ++ks) acc += __ldcg(partial + (int64_t)ks * bb + (int64_t)i * b + j);
+    srow[j] = acc;
+    s[(int64_t)i * b + j] = acc;
+  }
+  grid.sync();
+  const float di = srow[i];
+  {
+    int cr = 0, cc = 0;
+    for (int j = threadIdx.x; j < b; j += blockDim.x) {
+      const float r = srow[j], c = __ldcg(s + (int64_t)j * b + i);
+      cr += (r > di) || (r == di && j < i);
+      cc += (c > di) || (c == di && j < i);
+    }
+    cr = block_sum_int(cr, redi);
+    cc = block_sum_int(cc, redi);
+    if (threadIdx.x == 0) {
+      const float fb = (float)b;
+      rank_p[i] = 1.0f / (fb - (float)(cr + 1) + 1.0f) + 1.0f;
+      rank_b[i] = 1.0f / (fb - (float)(cc + 1) + 1.0f) + 1.0f;
+      diag[i] = di;
+    }
+  }
+  grid.sync();
+  {
+    const int64_t idi = ids[i];
+    float loss = 0.f, row_gp = 0.f;
+    int col_cnt = 0;
+    for (int j = threadIdx.x; j < b; j += blockDim.x) {
+      const bool same = ids[j] == idi;
+      const float sij = srow[j];
+      const float xp = margin + sij - di;                       // cost_p argument (d1 = S[i,i])
+      const float xb = margin + sij - __ldcg(diag + j);         // cost_b argument (d2 = S[j,j])
+      float g = 0.f;
+      if (!same) {
+        const float wp = __ldcg(rank_p + j), wb = __ldcg(rank_b + j);
+        loss += fmaxf(xp, 0.f) * wp + fmaxf(xb, 0.f) * wb;
+        if (xp >= 0.f) { g += wp; row_gp += wp; }               // torch.clamp backward passes the gradient at x == min
+        if (xb >= 0.f) g += wb;
+      }
+      if (ds != nullptr && j != i) ds[(int64_t)i * b + j] = scale * g;
+      const float xcol = margin + __ldcg(s + (int64_t)j * b + i) - di;      // column i: cost_b arguments that use S[i,i]
+      col_cnt += (!same && xcol >= 0.f) ? 1 : 0;
+    }
+    loss = block_sum_float(loss, redf);
+    row_gp = block_sum_float(row_gp, redf);
+    col_cnt = block_sum_int(col_cnt, redi);
+    if (threadIdx.x == 0) {
+      row_loss[i] = loss;
+      if (ds != nullptr) ds[(int64_t)i * b + i] = -scale * (row_gp + __ldcg(rank_b + i) * (float)col_cnt);
+    }
+  }
+  grid.sync();
+  if (blockIdx.x == 0) {
+    double v = 0.0;
+    for (int r = threadIdx.x; r < b; r += blockDim.x) v += (double)__ldcg(row_loss + r);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) redd[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += redd[w];
+      loss_out[0] = (float)(t * (double)scale);
+    }
+  }
+}
+
+// Can `blocks` blocks of the cooperative tile kernel be resident at once on this device?
+static bool triplet_tile_fits(int blocks, size_t smem) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, triplet_tile_kernel, 256, smem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return (long)per_sm * num_sms() >= blocks;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -461,6 +566,40 @@ int frx_triplet_fwd_bwd(const int64_t* brand_ids, const float* brand, const floa
   ts.ksplit_bytes = ks_bytes(b);
   const bool tc = tc_ok(b, b, d) && b % 4 == 0;
   const float scale = mean_style ? 1.0f / ((float)b * (float)b) : 1.0f;
+  // ---- fused path: 3 launches.  Tile GEMM with the 3xTF32 split inside the kernel and K split over the SMs (raw partial
+  // tiles) -> one cooperative kernel for the whole tile stage -> both gradient GEMMs in one grid (dS and the embeddings
+  // read in place, as K-major or transposed operands).
+  {
+    Gemm3xDesc gs{};
+    gs.a = post; gs.lda = d; gs.a_mn = 0; gs.b = brand; gs.ldb = d; gs.b_mn = 0;
+    gs.c = s; gs.ldc = b; gs.m = b; gs.n = b; gs.k = d; gs.alpha = 1.f;
+    Gemm3xDesc gg[2]{};
+    gg[0].a = ds; gg[0].lda = b; gg[0].a_mn = 0; gg[0].b = brand; gg[0].ldb = d; gg[0].b_mn = 1;     // dPost  = dS   . brand
+    gg[0].c = d_post; gg[0].ldc = d; gg[0].m = b; gg[0].n = d; gg[0].k = b; gg[0].alpha = 1.f;
+    gg[1].a = ds; gg[1].lda = b; gg[1].a_mn = 1; gg[1].b = post; gg[1].ldb = d; gg[1].b_mn = 1;      // dBrand = dS^T . post
+    gg[1].c = d_brand; gg[1].ldc = d; gg[1].m = b; gg[1].n = d; gg[1].k = b; gg[1].alpha = 1.f;
+    const size_t tile_smem = (size_t)b * sizeof(float);
+    static const bool fused_off = getenv("FRX_LOSS_UNFUSED") != nullptr;
+    if (!fused_off && gemm3x_supported(gs) && gemm3x_supported(gg[0]) && gemm3x_supported(gg[1]) && tile_smem <= 40 * 1024 &&
+        triplet_tile_fits(b, tile_smem)) {
+      int ksplit = gemm3x_plan_ksplit(&gs, 1);
+      const size_t avail = ts.ksplit_bytes / sizeof(float);
+      while (ksplit > 1 && gemm3x_partial_floats(&gs, 1, ksplit) > avail) --ksplit;
+      int rc = gemm3x_launch(st, &gs, 1, ksplit, true, reinterpret_cast<float*>(ts.ksplit), avail);
+      if (rc) return rc;
+      const float* part = reinterpret_cast<const float*>(ts.ksplit);
+      float* ds_arg = d_post ? ds : nullptr;
+      void* args[] = {(void*)&part, (void*)&ksplit, (void*)&b, (void*)&brand_ids, (void*)&margin, (void*)&scale, (void*)&s,
+                      (void*)&rank_p, (void*)&rank_b, (void*)&diag, (void*)&ds_arg, (void*)&partial, (void*)&loss};
+      FRX_CUDA(cudaLaunchCooperativeKernel((const void*)triplet_tile_kernel, dim3(b), dim3(256), args, tile_smem, st));
+      if (d_post) {
+        rc = gemm3x_launch(st, gg, 2, 1, false, nullptr, 0);
+        if (rc) return rc;
+      }
+      return FRX_OK;
+    }
+  }
+  // ---- general path (odd sizes, very large batches)
   // S[i,j] = post_i . brand_j   (loss.py:91-93)
   int rc = gemm_nt(st, tc, ts, post, false, d, brand, false, d, s, b, b, b, d, 1.f);
   if (rc) return rc;

@@ -366,6 +366,35 @@ def auc_rows(scores, row0, labels, seg_ptr, pos_sorted, best_score, best_index, 
     _lib.check(rc, "frx_auc_rows")
 
 
+def linear(x, weight, bias=None, col_scale=None, relu=False, out=None):
+    """Encoder-side Linear layer on the tensor cores: out = act((x @ weight.T) * col_scale + bias), fp32-grade (3xTF32
+    split inside the kernel).  x [M, K], weight [N, K] (nn.Linear layout), bias / col_scale [N] or None -- an eval-mode
+    BatchNorm1d folds into (col_scale, bias), see model.fold_batchnorm."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x", 2)
+    _req(weight, torch.float32, "weight", 2)
+    m, k = x.shape
+    n = weight.shape[0]
+    if weight.shape[1] != k:
+        raise ValueError("x is [*, %d] but weight is [*, %d]" % (k, weight.shape[1]))
+    for name, v in (("bias", bias), ("col_scale", col_scale)):
+        if v is not None:
+            _req(v, torch.float32, name, 1)
+            if v.numel() != n:
+                raise ValueError("%s has %d entries, expected %d" % (name, v.numel(), n))
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    if m == 0:
+        return out
+    need = lib.frx_linear_workspace_bytes(m, n, k)
+    ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.frx_linear(_ptr(x), x.stride(0), _ptr(weight), weight.stride(0), _ptr(col_scale), _ptr(bias), int(bool(relu)),
+                            m, n, k, _ptr(out), out.stride(0), _ptr(ws), need, _stream(x))
+    _lib.check(rc, "frx_linear")
+    return out
+
+
 SCORER_KINDS = {"P": 0, "AP": 1, "RR": 2, "NDCG": 3, "DCG": 4}
 _LOG2_TABLES = {}
 

@@ -221,6 +221,19 @@ int frx_pack_rank_stats(const int32_t* n_pos, const int32_t* first_in_list, cons
                         const unsigned long long* hit_mask, const unsigned long long* auc_num, int nb, int all_valid,
                         long long* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Encoder-side Linear layers (model.py:59-83 MFC, :463-491 PrjHeadFusionEncoder):
+ *      out[m, n] = act( (sum_k x[m, k] * w[n, k]) * col_scale[n] + col_shift[n] )
+ * i.e. nn.Linear (w = weight [n, k], col_shift = bias), with an eval-mode BatchNorm1d folded into col_scale / col_shift
+ * and an optional ReLU, as ONE fp32-grade tensor-core GEMM (3xTF32 split inside the kernel, tcgen05 kind::tf32, fp32
+ * accumulation) -- no cuBLAS call, no intermediate activation tensor.  x [m, ld_x], w [n, ld_w] fp32 row-major, 16-byte
+ * aligned, pitches multiples of 4 floats; col_scale / col_shift [n] or NULL; workspace only for small outputs whose K range
+ * is split over idle SMs (frx_linear_workspace_bytes). */
+size_t frx_linear_workspace_bytes(int m, int n, int k);
+int frx_linear(const float* x, int64_t ld_x, const float* w, int64_t ld_w, const float* col_scale, const float* col_shift,
+               int relu, int m, int n, int k, float* out, int64_t ld_out, void* workspace, size_t workspace_bytes,
+               void* stream);
+
 /* frx_metric_scores (A10; util/metric.py:6-123): the reference's rank-metric scorers over a BATCH of sorted label lists,
  * one warp per list.  labels int32 [n_lists, ld] (graded relevance, list i occupies labels[i*ld .. i*ld + lengths[i]);
  * lengths NULL = every list has max_len entries).  kind: 0 P@k (PrecisionScorer), 1 AP@k (APScorer), 2 RR (RRScorer),
