@@ -11,7 +11,7 @@
 // One CTA = one 128 x 128 output tile (x one K range when K is split), 384 threads, warp-specialised:
 //   warp 0 (one lane)   TMA producer: raw fp32 tiles {A 128 x 32, B 128 x 32} into a 3-stage ring.  K-major sources are
 //                       loaded with SWIZZLE_128B (the layout the MMA reads), MN-major sources as plain [32 k][128 rows];
-//   warps 4-11          converters: x -> hi = tf32(x), lo = tf32(x - hi), written as FOUR tiles (A_hi, A_lo, B_hi, B_lo) in
+//   warps 4-11          converters: x -> hi = tf32(x), lo = x - hi (Dekker split), written as FOUR tiles (A_hi, A_lo, B_hi, B_lo) in
 //                       the SWIZZLE_128B K-major layout (MN-major sources are transposed on the way: lane = row, four
 //                       k-consecutive scalar reads -> one swizzled 16-byte write), 2-stage ring, fence.proxy.async;
 //   warp 1 (one lane)   tcgen05.mma kind::tf32, M = N = 128, K = 8: per k-block 3 products x 4 instructions
@@ -48,16 +48,20 @@ struct Problem {
 };
 struct Params { Problem p[2]; int count; };
 
-__device__ __forceinline__ float cvt_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// x = hi + lo with hi exactly representable in tf32 (11 significant bits, round to nearest): Dekker's split with the
+// constant 2^13 + 1 -- three full-rate fp32 operations (cvt.rna.tf32.f32 runs on the quarter-rate conversion pipe and
+// made the converters, not the tensor core, the bottleneck: 1.1 us per k-block).  lo = x - hi is exact in fp32 and has
+// at most 13 significant bits; the tensor core reads its leading 11, so x is represented to 2^-22 relative.
+__device__ __forceinline__ void split1(float x, float& h, float& l) {
+  const float p = __fmul_rn(x, 8193.0f);          // _rn intrinsics: never contracted into an FMA (which would skip
+  h = __fsub_rn(p, __fsub_rn(p, x));              // the rounding of p that the split relies on)
+  l = __fsub_rn(x, h);
 }
 __device__ __forceinline__ void split4(const float4& v, float4& h, float4& l) {
-  h.x = cvt_tf32(v.x); l.x = cvt_tf32(v.x - h.x);
-  h.y = cvt_tf32(v.y); l.y = cvt_tf32(v.y - h.y);
-  h.z = cvt_tf32(v.z); l.z = cvt_tf32(v.z - h.z);
-  h.w = cvt_tf32(v.w); l.w = cvt_tf32(v.w - h.w);
+  split1(v.x, h.x, l.x);
+  split1(v.y, h.y, l.y);
+  split1(v.z, h.z, l.z);
+  split1(v.w, h.w, l.w);
 }
 // raw tile already in the SWIZZLE_128B K-major layout: the split is elementwise, offsets carry over
 __device__ __forceinline__ void convert_kmajor(const uint8_t* raw, uint8_t* hi, uint8_t* lo, int t) {

@@ -364,8 +364,35 @@ struct TcScratch {
 
 static bool tc_ok(int m, int n, int k) { return k % 4 == 0 && m >= 32 && n >= 32; }
 
+static Gemm3xDesc g3_desc(const float* x, bool xt, int64_t ldx, const float* y, bool yt, int64_t ldy, float* c, int64_t ldc,
+                          int m, int n, int k, float alpha) {
+  Gemm3xDesc g{};
+  g.a = x; g.lda = ldx; g.a_mn = xt ? 1 : 0;
+  g.b = y; g.ldb = ldy; g.b_mn = yt ? 1 : 0;
+  g.c = c; g.ldc = ldc; g.m = m; g.n = n; g.k = k; g.alpha = alpha;
+  return g;
+}
+
+static const bool g_loss_unfused = getenv("FRX_LOSS_UNFUSED") != nullptr;   // A/B switch: the round-1 split + GEMM chain
+
+// One or two independent products in ONE launch of the in-kernel-split GEMM (+ one reduction launch per product when the
+// outputs are so few tiles that K is split over the SMs).  Returns FRX_E_UNSUPPORTED when an operand layout rules it out.
+static int gemm3x_run(cudaStream_t st, const TcScratch& ws, const Gemm3xDesc* g, int count) {
+  for (int i = 0; i < count; ++i)
+    if (!gemm3x_supported(g[i])) return FRX_E_UNSUPPORTED;
+  int ksplit = gemm3x_plan_ksplit(g, count);
+  const size_t avail = ws.ksplit_bytes / sizeof(float);
+  while (ksplit > 1 && gemm3x_partial_floats(g, count, ksplit) > avail) --ksplit;
+  return gemm3x_launch(st, g, count, ksplit, false, reinterpret_cast<float*>(ws.ksplit), avail);
+}
+
 static int gemm_nt(cudaStream_t st, bool tc, const TcScratch& ws, const float* x, bool xt, int64_t ldx, const float* y, bool yt,
                    int64_t ldy, float* c, int64_t ldc, int m, int n, int k, float alpha) {
+  if (tc && !g_loss_unfused) {
+    const Gemm3xDesc g = g3_desc(x, xt, ldx, y, yt, ldy, c, ldc, m, n, k, alpha);
+    const int rc = gemm3x_run(st, ws, &g, 1);
+    if (rc != FRX_E_UNSUPPORTED) return rc;
+  }
   if (tc) {
     if (xt) launch_split_transpose(x, k, m, ldx, 1.0f, 0, ws.xa, st); else launch_split_rows(x, nullptr, m, k, ldx, 1.0f, 0, ws.xa, st);
     if (yt) launch_split_transpose(y, k, n, ldy, 1.0f, 1, ws.yb, st); else launch_split_rows(y, nullptr, n, k, ldy, 1.0f, 1, ws.yb, st);
@@ -579,8 +606,7 @@ int frx_triplet_fwd_bwd(const int64_t* brand_ids, const float* brand, const floa
     gg[1].a = ds; gg[1].lda = b; gg[1].a_mn = 1; gg[1].b = post; gg[1].ldb = d; gg[1].b_mn = 1;      // dBrand = dS^T . post
     gg[1].c = d_brand; gg[1].ldc = d; gg[1].m = b; gg[1].n = d; gg[1].k = b; gg[1].alpha = 1.f;
     const size_t tile_smem = (size_t)b * sizeof(float);
-    static const bool fused_off = getenv("FRX_LOSS_UNFUSED") != nullptr;
-    if (!fused_off && gemm3x_supported(gs) && gemm3x_supported(gg[0]) && gemm3x_supported(gg[1]) && tile_smem <= 40 * 1024 &&
+    if (!g_loss_unfused && gemm3x_supported(gs) && gemm3x_supported(gg[0]) && gemm3x_supported(gg[1]) && tile_smem <= 40 * 1024 &&
         triplet_tile_fits(b, tile_smem)) {
       int ksplit = gemm3x_plan_ksplit(&gs, 1);
       const size_t avail = ts.ksplit_bytes / sizeof(float);
@@ -681,9 +707,15 @@ int frx_contrastive_fwd_bwd(const float* brand, const float* post, int b, int d,
                                             weight, partial);
   reduce_partials_kernel<<<1, 256, 0, st>>>(partial, b, scale, loss);
   if (d_post) {
-    rc = gemm_nt(st, tc, ts, inter, false, b, pn, true, d, dbn, d, b, d, b, inv_t);        // d_bn = dInter   . pn / T
-    if (rc) return rc;
-    rc = gemm_nt(st, tc, ts, inter, true, b, bn, true, d, t1, d, b, d, b, inv_t);          // t1   = dInter^T . bn / T
+    // d_bn = dInter . pn / T  and  t1 = dInter^T . bn / T : one grid
+    const Gemm3xDesc gp[2] = {g3_desc(inter, false, b, pn, true, d, dbn, d, b, d, b, inv_t),
+                              g3_desc(inter, true, b, bn, true, d, t1, d, b, d, b, inv_t)};
+    rc = (tc && !g_loss_unfused) ? gemm3x_run(st, ts, gp, 2) : FRX_E_UNSUPPORTED;
+    if (rc == FRX_E_UNSUPPORTED) {
+      rc = gemm_nt(st, tc, ts, inter, false, b, pn, true, d, dbn, d, b, d, b, inv_t);
+      if (rc) return rc;
+      rc = gemm_nt(st, tc, ts, inter, true, b, bn, true, d, t1, d, b, d, b, inv_t);
+    }
     if (rc) return rc;
     const float* sum2 = nullptr;
     const float* sum3 = nullptr;

@@ -4,10 +4,17 @@
   L1Penalty     model.py:389-402   (identity forward; backward adds 1e-4 * sign(input))
   BrandAspects  model.py:406-428   (same parameters / state_dict keys; .forward keeps the [B, A, D]
                                     contract, .embed() is the fused (W.E)/A kernel used at eval time)
+  MFC           model.py:59-83     Linear + ReLU (+ dropout): eval path = ONE tensor-core GEMM with the bias / ReLU
+                                    epilogue (ops.linear -> frx_linear, 3xTF32 split inside the kernel)
+  PrjHeadFusionEncoder model.py:463-491  concat -> fc1 -> BatchNorm1d -> ReLU -> fc2: eval path = concat kernel + two
+                                    GEMMs, the BatchNorm folded into the first one's scale / shift epilogue
   FancyRec      model.py:538-649   shell only: brand side + post finalisation are ours, the learned
                                     visual / text / fusion encoders (out of scope) are
                                     injected by the caller, e.g. the reference's own classes.
+Same parameter names / state_dict keys as the reference classes, so reference checkpoints load unchanged.  Training
+(autograd) runs the reference's torch formulas; the fused kernels serve the no-grad path that encode_data takes.
 """
+import numpy as np
 import torch
 import torch.nn as nn
 from torch.autograd import Function
@@ -25,6 +32,80 @@ def l2norm(X):
         norm = torch.pow(X, 2).sum(dim=1, keepdim=True).sqrt()
         return torch.div(X, norm)
     return ops.finalize_posts(X.contiguous().float(), final_norm=True, want_f32=True, want_bf16=False)[0]
+
+
+def xavier_init_fc(fc, bias=True):
+    """Xavier initialization for the fully connected layer (model.py:47-54)."""
+    r = np.sqrt(6.) / np.sqrt(fc.in_features + fc.out_features)
+    fc.weight.data.uniform_(-r, r)
+    if bias:
+        fc.bias.data.fill_(0)
+
+
+def _fused_ok(module, x):
+    """The kernels serve inference: eval mode, no autograd graph wanted, CUDA fp32 input."""
+    return (not module.training) and (not torch.is_grad_enabled() or not x.requires_grad) and x.is_cuda and \
+        x.dtype == torch.float32 and x.dim() == 2
+
+
+def fold_batchnorm(bn):
+    """Eval-mode BatchNorm1d as a per-column (scale, shift): y = x * scale + shift."""
+    scale = (bn.weight if bn.affine else torch.ones_like(bn.running_var)) / torch.sqrt(bn.running_var + bn.eps)
+    shift = (bn.bias if bn.affine else torch.zeros_like(bn.running_mean)) - bn.running_mean * scale
+    return scale.detach().float().contiguous(), shift.detach().float().contiguous()
+
+
+class MFC(nn.Module):
+    """Multi Fully Connected Layers (model.py:59-83): fc1 -> ReLU -> dropout."""
+
+    def __init__(self, fc_layers, dropout):
+        super(MFC, self).__init__()
+        self.fc1 = nn.Linear(fc_layers[0], fc_layers[1])
+        self.dropout = nn.Dropout(p=dropout)
+        self.relu = nn.ReLU()
+        self.init_weights()
+
+    def init_weights(self):
+        xavier_init_fc(self.fc1)
+
+    def forward(self, inputs):
+        if _fused_ok(self, inputs):      # eval: dropout is the identity; bias + ReLU live in the GEMM epilogue
+            return ops.linear(inputs.contiguous(), self.fc1.weight.detach(), bias=self.fc1.bias.detach(), relu=True)
+        return self.dropout(self.relu(self.fc1(inputs)))
+
+
+class PrjHeadFusionEncoder(nn.Module):
+    """Non-linear projection head over the concatenated branches (model.py:463-491)."""
+
+    def __init__(self, opt):
+        super(PrjHeadFusionEncoder, self).__init__()
+        self.opt = opt
+        self.common_embedding_size = opt.common_embedding_size
+        self.visual_mapping_size = opt.visual_mapping_size[1]
+        self.text_mapping_size = opt.text_mapping_size[1]
+        self.fc1 = nn.Linear(self.text_mapping_size + self.visual_mapping_size, 512, bias=False)
+        self.fc2 = nn.Linear(512, self.common_embedding_size, bias=True)
+        self.projection_head = nn.Sequential(self.fc1, nn.BatchNorm1d(512), nn.ReLU(), self.fc2)
+        self.init_weights()
+
+    def forward(self, visual_embs, text_embs):
+        if _fused_ok(self, visual_embs) and _fused_ok(self, text_embs):
+            # concat in one pass of the finalisation kernel (no norms), then fc1 (+ folded BatchNorm + ReLU) and fc2 (+ bias)
+            fusion_vt = ops.finalize_posts(visual_embs.contiguous(), text_embs.contiguous(), final_norm=False,
+                                           want_f32=True, want_bf16=False)[0]
+            if self.opt.prj_head_output:
+                return fusion_vt
+            scale, shift = fold_batchnorm(self.projection_head[1])
+            hidden = ops.linear(fusion_vt, self.fc1.weight.detach(), bias=shift, col_scale=scale, relu=True)
+            return ops.linear(hidden, self.fc2.weight.detach(), bias=self.fc2.bias.detach())
+        fusion_vt = torch.cat((visual_embs, text_embs), 1)
+        if self.opt.prj_head_output:
+            return fusion_vt
+        return self.projection_head(fusion_vt)
+
+    def init_weights(self):
+        xavier_init_fc(self.fc1, bias=False)
+        xavier_init_fc(self.fc2)
 
 
 class L1Penalty(Function):

@@ -371,8 +371,11 @@ def linear(x, weight, bias=None, col_scale=None, relu=False, out=None):
     split inside the kernel).  x [M, K], weight [N, K] (nn.Linear layout), bias / col_scale [N] or None -- an eval-mode
     BatchNorm1d folds into (col_scale, bias), see model.fold_batchnorm."""
     lib = _lib.load()
-    _req(x, torch.float32, "x", 2)
-    _req(weight, torch.float32, "weight", 2)
+    for name, t in (("x", x), ("weight", weight)) + ((("out", out),) if out is not None else ()):
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise _lib.FrxError("%s must be a CUDA tensor (fancyrec_b200 has no CPU fallback)" % name)
+        if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+            raise ValueError("%s must be a 2-D float32 tensor with unit column stride (row pitch is free)" % name)
     m, k = x.shape
     n = weight.shape[0]
     if weight.shape[1] != k:

@@ -247,9 +247,45 @@ def gen_bigfile():
     print("wrote bigfile.json")
 
 
+# ----------------------------------------------------------------------------
+# 6. encoder-side Linear layers: MFC and PrjHeadFusionEncoder in eval mode
+# ----------------------------------------------------------------------------
+def gen_encoder_layers():
+    torch.manual_seed(1234)
+    out = {}
+    mfc = ref_model.MFC([300, 200], 0.2).eval()
+    with torch.no_grad():
+        mfc.fc1.bias.copy_(torch.randn(200) * 0.1)
+    x = torch.from_numpy(synth.gaussian(611, 37, 300))
+    with torch.no_grad():
+        out["mfc_out"] = mfc(x).numpy()
+    for k, v in mfc.state_dict().items():
+        out["mfc." + k] = v.numpy()
+    opt = types.SimpleNamespace(common_embedding_size=96, visual_mapping_size=[0, 120], text_mapping_size=[0, 72],
+                                prj_head_output=False)
+    head = ref_model.PrjHeadFusionEncoder(opt).eval()
+    bn = head.projection_head[1]
+    with torch.no_grad():                      # a BatchNorm that has seen data: non-trivial statistics and affine terms
+        bn.running_mean.copy_(torch.randn(512) * 0.05)
+        bn.running_var.copy_(torch.rand(512) * 0.5 + 0.5)
+        bn.weight.copy_(torch.rand(512) + 0.5)
+        bn.bias.copy_(torch.randn(512) * 0.1)
+        head.fc2.bias.copy_(torch.randn(96) * 0.1)
+    v = torch.from_numpy(synth.gaussian(612, 41, 120))
+    t = torch.from_numpy(synth.gaussian(613, 41, 72))
+    with torch.no_grad():
+        out["head_out"] = head(v, t).numpy()
+        opt.prj_head_output = True
+        out["head_concat"] = head(v, t).numpy()
+    for k, val in head.state_dict().items():
+        out["head." + k] = val.numpy()
+    save("encoder_layers.npz", **out)
+
+
 if __name__ == "__main__":
     gen_ndcg_metric()
     gen_ranking()
     gen_losses()
     gen_finalize()
     gen_bigfile()
+    gen_encoder_layers()
