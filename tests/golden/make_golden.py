@@ -278,7 +278,8 @@ def gen_encoder_layers():
         opt.prj_head_output = True
         out["head_concat"] = head(v, t).numpy()
     for k, val in head.state_dict().items():
-        out["head." + k] = val.numpy()
+        if not k.startswith(("projection_head.0.", "projection_head.3.")):      # the same tensors as fc1 / fc2
+            out["head." + k] = val.numpy()
     save("encoder_layers.npz", **out)
 
 
