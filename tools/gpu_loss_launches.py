@@ -47,3 +47,34 @@ def t_f():
 timed("triplet fwd+bwd", t_fb)
 timed("triplet fwd (no_grad)", t_f)
 timed("contrastive fwd+bwd", c_fb)
+
+
+# ---- device time without host gaps: the C entry point captured into a CUDA graph and replayed
+from fancyrec_b200 import ops
+
+
+def graph_us(fn, reps=50):
+    fn(); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    for _ in range(3):
+        g.replay()
+    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        g.replay()
+    e.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(e) / reps * 1e3
+
+
+bd, pd = brand.detach(), post.detach()
+W = torch.randn((3072, d), device=dev) / d ** 0.5
+print("triplet fwd+bwd  device (graph replay) %.1f us" % graph_us(lambda: ops.triplet_fwd_bwd(ids, bd, pd, 0.2, 0, True)))
+print("triplet fwd      device (graph replay) %.1f us" % graph_us(lambda: ops.triplet_fwd_bwd(ids, bd, pd, 0.2, 0, False)))
+keys = con.queue
+print("contrastive fwd+bwd device (graph replay) %.1f us" % graph_us(
+    lambda: ops.contrastive_fwd_bwd(bd, pd, keys, 0, False, 0.03, 0.8, 0, True)))
+print("linear 512x3072x3072 (MFC-sized) device %.1f us" % graph_us(lambda: ops.linear(pd, W)))
