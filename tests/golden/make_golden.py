@@ -283,6 +283,34 @@ def gen_encoder_layers():
     save("encoder_layers.npz", **out)
 
 
+# ----------------------------------------------------------------------------
+# 7. tester.py command line: every option of the reference parser with its default / type / choices
+# ----------------------------------------------------------------------------
+def gen_tester_cli():
+    import argparse
+    captured = {}
+    orig = argparse.ArgumentParser.parse_args
+
+    def spy(self, args=None, namespace=None):
+        captured["actions"] = [dict(dest=a.dest, option_strings=list(a.option_strings), default=a.default,
+                                    type=getattr(a.type, "__name__", None), choices=list(a.choices) if a.choices else None,
+                                    required=a.required)
+                               for a in self._actions if a.dest != "help"]
+        return orig(self, ["insCartest"], namespace)
+
+    sys.modules.setdefault("tensorboard_logger", types.ModuleType("tensorboard_logger"))
+    import tester as ref_tester
+    argparse.ArgumentParser.parse_args = spy
+    try:
+        ns = ref_tester.parse_args()
+    finally:
+        argparse.ArgumentParser.parse_args = orig
+    out = {"actions": captured["actions"], "parsed_defaults": vars(ns)}
+    with open(os.path.join(HERE, "tester_cli.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote tester_cli.json")
+
+
 if __name__ == "__main__":
     gen_ndcg_metric()
     gen_ranking()
@@ -290,3 +318,4 @@ if __name__ == "__main__":
     gen_finalize()
     gen_bigfile()
     gen_encoder_layers()
+    gen_tester_cli()
