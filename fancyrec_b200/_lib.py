@@ -66,6 +66,9 @@ SIGNATURES = {
     "frx_pack_rank_stats": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "frx_group_positives": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "frx_auc_rows": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "frx_brand_train_fwd": (c_i32, [c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, ctypes.c_uint64, c_vp, c_vp]),
+    "frx_brand_train_bwd": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, ctypes.c_uint64, c_vp, c_vp, c_vp]),
+    "frx_brand_dropout_mask": (c_i32, [c_i32, c_i32, c_i32, ctypes.c_uint64, c_vp, c_vp]),
     "frx_linear_workspace_bytes": (c_sz, [c_i32, c_i32, c_i32]),
     "frx_linear": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_sz, c_vp]),
     "frx_metric_scores": (c_i32, [c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),

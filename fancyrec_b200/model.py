@@ -120,6 +120,24 @@ class L1Penalty(Function):
         return input.sign().mul(0.0001) + grad_output
 
 
+class _BrandTrainFn(Function):
+    """Dropout(0.5) on the [B, A, D] products + mean over aspects + L1Penalty, fused (frx_brand_train_fwd / _bwd): the
+    keep bits are a counter-based hash of (seed, b, a, d), regenerated in the backward instead of stored."""
+
+    @staticmethod
+    def forward(ctx, w_rows, aspects, seed):
+        w_rows, aspects = w_rows.contiguous().float(), aspects.contiguous().float()
+        ctx.save_for_backward(w_rows, aspects)
+        ctx.seed = seed
+        return ops.brand_train_fwd(w_rows, aspects, seed)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        w_rows, aspects = ctx.saved_tensors
+        d_w, d_e = ops.brand_train_bwd(grad_out.contiguous().float(), w_rows, aspects, ctx.seed)
+        return d_w, d_e, None
+
+
 class BrandAspects(nn.Module):
     def __init__(self, opt):
         super(BrandAspects, self).__init__()
@@ -135,6 +153,16 @@ class BrandAspects(nn.Module):
         """[B] ids -> [B, A, D] weighted aspects (reference contract; training path with dropout)."""
         w = L1Penalty.apply(self.brand_embeddings(brand_list))
         return self.dropout(w.unsqueeze(2) * self.aspects_embeddings.unsqueeze(0))
+
+    def embed_train(self, brand_list, seed=None):
+        """Training-time [B, D] brand embedding = forward(brand_list).permute(1, 0, 2).mean(0) of the reference
+        (model.py:594) without the [B, A, D] intermediate: dropout(0.5) on the products and the L1Penalty gradient are
+        fused into the kernels.  `seed` fixes the dropout mask (default: drawn from torch's CPU generator)."""
+        if self.dropout.p != 0.5:
+            raise ValueError("the fused path implements nn.Dropout()'s default p = 0.5 (model.py:417)")
+        if seed is None:
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())
+        return _BrandTrainFn.apply(self.brand_embeddings(brand_list), self.aspects_embeddings, seed)
 
     def embed(self, brand_list):
         """Eval-time fast path: mean over aspects -> [B, D] without materialising [B, A, D]."""
@@ -174,9 +202,11 @@ class FancyRec(nn.Module):
 
     def embed_brand(self, brand_ids, volatile=True):
         brand_ids = brand_ids.to(device)
-        if not self.brand_encoding.training and not torch.is_grad_enabled():
-            return self.brand_encoding.embed(brand_ids)
-        return self.brand_encoding(brand_ids).permute((1, 0, 2)).mean(0)
+        if not self.brand_encoding.training:
+            if not torch.is_grad_enabled():
+                return self.brand_encoding.embed(brand_ids)
+            return self.brand_encoding(brand_ids).permute((1, 0, 2)).mean(0)      # eval with autograd: no dropout, torch path
+        return self.brand_encoding.embed_train(brand_ids)                          # training: fused, no [B, A, D] tensor
 
     def embed_vis(self, vis_data, volatile=True):
         frames, mean_origin, video_lengths, vidoes_mask = vis_data

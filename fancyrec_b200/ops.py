@@ -154,6 +154,48 @@ def brand_embed(w, e, brand_ids=None, nb=None, tensor_cores=True):
     return out
 
 
+def brand_train_fwd(w_rows, e, seed):
+    """Training-time brand embedding with dropout(0.5) on the products, no [B, A, D] tensor: -> [B, D] fp32."""
+    lib = _lib.load()
+    _req(w_rows, torch.float32, "w_rows", 2)
+    _req(e, torch.float32, "e", 2)
+    b, a = w_rows.shape
+    if e.shape[0] != a:
+        raise ValueError("w_rows is [*, %d] but e is [%d, *]" % (a, e.shape[0]))
+    out = torch.empty((b, e.shape[1]), dtype=torch.float32, device=w_rows.device)
+    with torch.cuda.device(w_rows.device):
+        rc = lib.frx_brand_train_fwd(_ptr(w_rows), w_rows.stride(0), _ptr(e), b, a, e.shape[1], int(seed), _ptr(out),
+                                     _stream(w_rows))
+    _lib.check(rc, "frx_brand_train_fwd")
+    return out
+
+
+def brand_train_bwd(grad_out, w_rows, e, seed):
+    """-> (d_w_rows [B, A] incl. the L1Penalty term 1e-4 * sign(w), d_e [A, D]) for the mask of `seed`."""
+    lib = _lib.load()
+    _req(grad_out, torch.float32, "grad_out", 2)
+    _req(w_rows, torch.float32, "w_rows", 2)
+    _req(e, torch.float32, "e", 2)
+    b, a = w_rows.shape
+    d_w = torch.empty((b, a), dtype=torch.float32, device=w_rows.device)
+    d_e = torch.empty_like(e)
+    with torch.cuda.device(w_rows.device):
+        rc = lib.frx_brand_train_bwd(_ptr(grad_out), _ptr(w_rows), w_rows.stride(0), _ptr(e), b, a, e.shape[1], int(seed),
+                                     _ptr(d_w), _ptr(d_e), _stream(w_rows))
+    _lib.check(rc, "frx_brand_train_bwd")
+    return d_w, d_e
+
+
+def brand_dropout_mask(b, a, d, seed, device):
+    """The keep mask m(b, a, d) of `seed` as uint8 [B, A, D] (tests: parity with the reference formula under a fixed mask)."""
+    lib = _lib.load()
+    mask = torch.empty((b, a, d), dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        rc = lib.frx_brand_dropout_mask(b, a, d, int(seed), _ptr(mask), torch.cuda.current_stream(device).cuda_stream)
+    _lib.check(rc, "frx_brand_dropout_mask")
+    return mask
+
+
 # ---------------------------------------------------------------------------------------------
 def _operands(brand_op, post_op, d):
     """Operands are both bf16 (default precision) or both fp32 (tf32 tensor-core path)."""

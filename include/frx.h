@@ -222,6 +222,21 @@ int frx_pack_rank_stats(const int32_t* n_pos, const int32_t* first_in_list, cons
                         long long* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * A4, training path: BrandAspects.forward + mean over aspects WITH dropout(0.5) on the [B, A, D] products
+ * (model.py:419-428, :594) and its backward incl. L1Penalty.backward (model.py:395-401), never materialising [B, A, D]:
+ *      out[b, d]     = (2 / A) * sum_a w_rows[b, a] * E[a, d] * m(b, a, d)
+ *      d_w_rows[b,a] = (2 / A) * sum_d g[b, d] * E[a, d] * m(b, a, d) + 1e-4 * sign(w_rows[b, a])
+ *      d_e[a, d]     = (2 / A) * sum_b g[b, d] * w_rows[b, a] * m(b, a, d)
+ * w_rows [b, ld_w] = the embedding rows of the batch (the caller gathers them; autograd scatters d_w_rows back).
+ * m(b, a, d) in {0, 1} is a counter-based hash of (seed, b, a, d), identical in all three kernels for one seed;
+ * frx_brand_dropout_mask writes it out as uint8 [b, a, d] (tests only). */
+int frx_brand_train_fwd(const float* w_rows, int64_t ld_w, const float* e, int b, int a, int d, uint64_t seed, float* out,
+                        void* stream);
+int frx_brand_train_bwd(const float* grad_out, const float* w_rows, int64_t ld_w, const float* e, int b, int a, int d,
+                        uint64_t seed, float* d_w_rows, float* d_e, void* stream);
+int frx_brand_dropout_mask(int b, int a, int d, uint64_t seed, uint8_t* mask, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Encoder-side Linear layers (model.py:59-83 MFC, :463-491 PrjHeadFusionEncoder):
  *      out[m, n] = act( (sum_k x[m, k] * w[n, k]) * col_scale[n] + col_shift[n] )
  * i.e. nn.Linear (w = weight [n, k], col_shift = bias), with an eval-mode BatchNorm1d folded into col_scale / col_shift
