@@ -142,5 +142,5 @@ def test_cli_flow_on_a_reference_layout_checkpoint(tmp_path, capsys):
     marker = tmp_path / "insCartest" / "results" / "insCartrain" / "run0" / "model_best.pth.tar" / "pred_errors_matrix.pth.tar"
     marker.write_text("x")
     with pytest.raises(SystemExit) as ex:
-        tester.main(argv[:3] + ["0"] + argv[4:], build=_build(n, dv, dt, nb, seed=5))
+        tester.main(argv[:4] + ["0"] + argv[5:], build=_build(n, dv, dt, nb, seed=5))
     assert ex.value.code == 0
