@@ -38,7 +38,7 @@ def sim_tile(brand, post):
     return np.asarray(post, np.float64) @ np.asarray(brand, np.float64).T
 
 
-def triplet_loss(brand_ids, brand, post, margin=0.0, cost_style='sum'):
+def triplet_loss(brand_ids, brand, post, margin=0.0, cost_style='sum', s_override=None):
     """Returns (loss, d_brand, d_post, aux).  loss.py:87-143 with direction='all'.
     max_violation / measure / loss_fun are accepted by the reference constructor and
     never read in forward (loss.py:79-85 vs :87-143) -- there is nothing to restate."""
@@ -46,7 +46,9 @@ def triplet_loss(brand_ids, brand, post, margin=0.0, cost_style='sum'):
     post = np.asarray(post, np.float64)
     ids = np.asarray(brand_ids)
     b = brand.shape[0]
-    s = sim_tile(brand, post)
+    # s_override: evaluate everything downstream of the tile on a GIVEN tile (the tests pass the device's own fp32
+    # tile, so that the integer ranks and the hinge active set are decided on identical numbers)
+    s = sim_tile(brand, post) if s_override is None else np.asarray(s_override, np.float64)
     s32 = s.astype(np.float32)
     rank_p, pos_r = _rank_weight_rows(s32)
     rank_b, pos_c = _rank_weight_cols(s32)
@@ -70,7 +72,7 @@ def triplet_loss(brand_ids, brand, post, margin=0.0, cost_style='sum'):
     d_post = ds @ brand
     d_brand = ds.T @ post
     return loss, d_brand, d_post, dict(s=s, ds=ds, rank_p=rank_p, rank_b=rank_b,
-                                       pos_r=pos_r, pos_c=pos_c)
+                                       pos_r=pos_r, pos_c=pos_c, active_p=~(mask | (xp < 0)), active_b=~(mask | (xb < 0)))
 
 
 def _normalize(x, eps=1e-12):

@@ -34,20 +34,40 @@ def test_triplet_golden(golden_dir, style):
             floss.TripletLoss(margin=0.2, direction=direction)(torch.from_numpy(ids), to_dev(brand), to_dev(post))
 
 
-@pytest.mark.parametrize("b,d", [(512, 1024), (100, 96), (257, 300)])
+@pytest.mark.parametrize("b,d", [(512, 1024), (512, 3072), (100, 96), (257, 300)])
 def test_triplet_vs_oracle_config3(b, d):
+    """Values and decisions are tested SEPARATELY.  (1) the tile: |S_device - S_fp64| <= 1e-5 of its scale (3xTF32);
+    (2) everything downstream of the tile -- integer rank weights, hinge active set, dS, both gradient GEMMs, the loss --
+    against the fp64 oracle evaluated on the device's OWN tile: 1e-5 of the gradient scale; (3) the decisions taken on the
+    device tile differ from those taken on the fp64 tile only where a hinge argument is within rounding of zero
+    (a handful of the B^2 terms), and the end-to-end loss agrees to 2e-5."""
     from fancyrec_b200 import ops
     rs = np.random.RandomState(b + d)
     ids = rs.randint(0, 51, b).astype(np.int64)
     brand = (rs.standard_normal((b, d)) * 0.05).astype(np.float32)
     post = (rs.standard_normal((b, d)) * 0.05).astype(np.float32) + brand * 0.5
+    aligned = d % 4 == 0
+    s_dev = ops.linear(to_dev(post), to_dev(brand)).cpu().numpy() if aligned else None      # the tile the loss kernel sees
     for style in (0, 1):
         loss, db, dp = ops.triplet_fwd_bwd(to_dev(ids), to_dev(brand), to_dev(post), 0.2, style)
-        wl, wdb, wdp, aux = oloss.triplet_loss(ids, brand, post, 0.2, 'mean' if style else 'sum')
-        np.testing.assert_allclose(loss.item(), wl, rtol=2e-4)
-        scale = np.abs(wdb).max()
-        np.testing.assert_allclose(db.cpu().numpy(), wdb, rtol=2e-3, atol=2e-3 * scale)
-        np.testing.assert_allclose(dp.cpu().numpy(), wdp, rtol=2e-3, atol=2e-3 * np.abs(wdp).max())
+        name = 'mean' if style else 'sum'
+        wl, wdb, wdp, aux = oloss.triplet_loss(ids, brand, post, 0.2, name)
+        np.testing.assert_allclose(loss.item(), wl, rtol=2e-5)
+        if s_dev is not None:
+            assert np.abs(s_dev - aux["s"]).max() <= 1e-5 * np.abs(aux["s"]).max()
+            ol, odb, odp, oaux = oloss.triplet_loss(ids, brand, post, 0.2, name, s_override=s_dev)
+            np.testing.assert_allclose(loss.item(), ol, rtol=1e-5)
+            np.testing.assert_allclose(db.cpu().numpy(), odb, rtol=0, atol=1e-5 * np.abs(odb).max())
+            np.testing.assert_allclose(dp.cpu().numpy(), odp, rtol=0, atol=1e-5 * np.abs(odp).max())
+            flips = int((oaux["active_p"] != aux["active_p"]).sum() + (oaux["active_b"] != aux["active_b"]).sum())
+            assert flips <= max(4, b * b // 20000), flips
+            assert np.array_equal(oaux["rank_p"], aux["rank_p"]) or np.abs(oaux["rank_p"] - aux["rank_p"]).max() < 0.5
+        else:                                         # odd width: fp32 FMA fallback, summation-order tolerance
+            np.testing.assert_allclose(db.cpu().numpy(), wdb, rtol=2e-3, atol=2e-3 * np.abs(wdb).max())
+            np.testing.assert_allclose(dp.cpu().numpy(), wdp, rtol=2e-3, atol=2e-3 * np.abs(wdp).max())
+        # forward-only call (no_grad path): same loss, no gradient work
+        loss_f, none_b, none_p = ops.triplet_fwd_bwd(to_dev(ids), to_dev(brand), to_dev(post), 0.2, style, want_grad=False)
+        assert none_b is None and none_p is None and loss_f.item() == loss.item()
 
 
 def test_triplet_upstream_gradient_scales():
