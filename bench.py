@@ -244,6 +244,9 @@ def run_ours(args):
     cfg = dict(CFG)
     nb, n_local = args.brands, args.posts_per_gpu
     d = cfg["dv"] + cfg["dt"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                  # nvidia-smi needs a few 100 ms to start reporting: start before the workload is built
     w, e, labels, visual, text = make_workload(dev, rank, nb, n_local, cfg)
     overlap = os.environ.get("FRX_OVERLAP", "0") == "1"   # measured slower on B200: off
     pipe = pipeline.EvalPipeline(dev, nb, n_local, cfg["dv"], cfg["dt"], k=cfg["k"], n_posts_total=n_local * world,
@@ -252,9 +255,6 @@ def run_ours(args):
     pk = peaks()
     warmup = max(args.warmup, 3)
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()                  # nvidia-smi needs ~100 ms to start reporting: start before warm-up
     for _ in range(warmup):
         result = pipe.result(pipe.submit(*inputs))
     barrier_sync(world)
