@@ -173,8 +173,9 @@ int frx_score_count_tf32(const float* brand_f32, int64_t ld_a, const float* post
                          unsigned long long* count_out, void* stream);
 
 /* Merge G candidate lists per brand (the multi-GPU exchange step after the all-gather):
- * in_scores / in_index [g, nb, k_in] -> out [nb, k_out], same order; entries with index < 0 are
- * padding.  Requires g * k_in <= 16384. */
+ * in_scores / in_index [g, nb, k_in] -> out [nb, k_out], same order.  Every input list must be sorted under the total
+ * order (score desc, index asc) with its padding entries (index < 0) at the tail -- i.e. be a list frx_score_topk or this
+ * function produced; a post appears in at most one list.  Requires g * k_in <= 16384. */
 int frx_topk_merge(const float* in_scores, const int32_t* in_index, int g, int nb, int k_in,
                    float* out_scores, int32_t* out_index, int k_out, void* stream);
 /* Same, reading shard r's [nb, k_in] lists at in_scores + r * shard_stride / in_index + r * shard_stride (elements):
