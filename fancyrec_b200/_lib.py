@@ -83,6 +83,7 @@ SIGNATURES = {
     "frx_lab_fwd_bwd": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "frx_normalize_rows": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp]),
     "frx_set_cta_pairs": (c_i32, [c_i32]),
+    "frx_set_cluster": (c_i32, [c_i32]),
     "frx_probe_enable": (c_i32, [c_i32]),
     "frx_probe_read": (c_i32, [c_vp, c_i32]),
 }

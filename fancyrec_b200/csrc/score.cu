@@ -308,8 +308,16 @@ __device__ __forceinline__ void store_dense_chunk_staged(float* base, int64_t ld
   }
 }
 
-template <int MODE, bool TF32, bool PAIR>
+// CL > 1 (with PAIR = false): a cluster of CL CTAs works on CL consecutive m-tiles of the SAME post range.  Every CTA runs
+// its own cta_group::1 MMAs on its own A tile, but the B tile is fetched ONCE per cluster: CTA c loads rows
+// [c * 256 / CL, (c + 1) * 256 / CL) of it and TMA-multicasts them into the shared memory of all CL CTAs.  A ring slot is
+// free when ALL CTAs have consumed it (multicast MMA commits, `empty` counts CL arrivals).  Sharing the post operand no
+// longer depends on the CTAs of a range running in lock step so that their L2 reads coalesce.
+template <int MODE, bool TF32, bool PAIR, int CL>
 __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ScoreParams& P) {
+  static_assert(!(PAIR && CL > 1), "the CTA-pair variant and the multicast clusters are separate variants");
+  constexpr bool CLUSTERED = PAIR || CL > 1;
+  constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
   using R = Ring<PAIR>;
   constexpr int STAGES = R::STAGES;
   constexpr int B_STAGE = R::B_BYTES;
@@ -326,7 +334,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
     if (threadIdx.x == 0) {
       prefetch_tmap(&tmap_a);
       prefetch_tmap(&tmap_b);
-      for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&tail->full[s]), 1); mbar_init(smem_u32(&tail->empty[s]), 1); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&tail->full[s]), 1); mbar_init(smem_u32(&tail->empty[s]), CL); }
       for (int s = 0; s < 2; ++s) {
         mbar_init(smem_u32(&tail->tmem_full[s]), 1);
         mbar_init(smem_u32(&tail->tmem_empty[s]), NUM_EPI_WARPS * (PAIR ? 2 : 1));   // the leader hears both CTAs' epilogues
@@ -347,25 +355,29 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
         if (__ldg(P.thr_index + r) >= 0) tail->tile_need[r / BM] = 1;
     }
     tc_fence_before();
-    if (PAIR) cluster_sync_all(); else __syncthreads();    // the peer's barriers are initialised before anything targets them
+    if (CLUSTERED) cluster_sync_all(); else __syncthreads();    // the peers' barriers are initialised before anything targets them
     tc_fence_after();
   }
   const uint32_t tid = threadIdx.x, bid = blockIdx.x, nbid = gridDim.x;
   const int warp = (int)(tid >> 5), lane = (int)(tid & 31);
   // CTA pair: cluster rank 0 = leader (issues the MMAs); the pair shares one scheduling slot and one 256-row m-unit
-  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
-  const int slot = PAIR ? (int)(bid >> 1) : (int)bid;
-  const int nslots = PAIR ? (int)(nbid >> 1) : (int)nbid;
-  const int m_units = PAIR ? (P.num_m_tiles >> 1) : P.num_m_tiles;   // the host pads num_m_tiles to even for pairs
+  constexpr int UNIT = PAIR ? 2 : CL;                      // m-tiles per scheduling unit (CTA, pair or cluster)
+  const uint32_t crank = CLUSTERED ? cluster_ctarank() : 0u;
+  const int slot = (int)bid / UNIT;
+  const int nslots = (int)nbid / UNIT;
+  const int m_units = P.num_m_tiles / UNIT;                // the host pads num_m_tiles to a multiple of UNIT
   const uint32_t tmem_base = tail->tmem_base;
 
   // item = (split * m_units + m_unit) * k_splits + ks ; a unit is one 128-row m-tile, or the pair's two m-tiles
   const int n_items = m_units * P.splits * P.k_splits;
   auto unit_skipped = [&](int mu) -> bool {                 // COUNT only; both CTAs of a pair take the same decision
     if (MODE != MODE_COUNT) return false;
-    const int t0_ = PAIR ? 2 * mu : mu, t1_ = PAIR ? 2 * mu + 1 : mu;
+    const int t0_ = mu * UNIT, t1_ = mu * UNIT + UNIT - 1;
     if (t1_ >= MAX_NEED_TILES) return false;
-    return !(tail->tile_need[t0_] | tail->tile_need[t1_]);
+    bool need = false;
+#pragma unroll
+    for (int t_ = 0; t_ < UNIT; ++t_) need = need || tail->tile_need[t0_ + t_];
+    return !need;
   };
 
   // Register redistribution: each role's code must be DOMINATED by its setmaxnreg -- ptxas budgets a region by the
@@ -379,7 +391,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
         const int ks = item % P.k_splits, mi = item / P.k_splits;
         const int mu = mi % m_units, split = mi / m_units;
         if (unit_skipped(mu)) continue;
-        const int m_tile = PAIR ? 2 * mu + (int)crank : mu;
+        const int m_tile = mu * UNIT + (int)crank;
         const int kb0 = P.num_k_blocks * ks / P.k_splits, kb1 = P.num_k_blocks * (ks + 1) / P.k_splits;
         const int64_t t0 = P.num_n_tiles * split / P.splits, t1 = P.num_n_tiles * (split + 1) / P.splits;
         for (int64_t t = t0; t < t1; ++t) {
@@ -393,6 +405,12 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
               const uint32_t lfb = mapa_shared(fb, 0);
               tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tmap_a, lfb, kb * BK, m_tile * BM);
               tma_load_2d_pair(smem_b + stage * B_STAGE, &tmap_b, lfb, kb * BK, (int32_t)(t * BN + crank * (BN / 2)));
+            } else if (CL > 1) {
+              // this CTA's own A tile + the whole B tile, which arrives as CL multicast slices (one from every CTA)
+              mbar_arrive_expect_tx(fb, R::STAGE_BYTES);
+              tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, fb, kb * BK, m_tile * BM);
+              tma_load_2d_multicast(smem_b + stage * B_STAGE + crank * (B_STAGE / CL), &tmap_b, fb, kb * BK,
+                                    (int32_t)(t * BN + crank * (BN / CL)), CL_MASK);
             } else {
               mbar_arrive_expect_tx(fb, R::STAGE_BYTES);
               tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, fb, kb * BK, m_tile * BM);
@@ -402,7 +420,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
           }
         }
       }
-      if (PAIR) {
+      if (CLUSTERED) {
         // drain: every multicast "slot free" arrival aimed at this CTA has landed before it may exit
         for (int i = 0; i < STAGES; ++i) {
           mbar_wait(smem_u32(&tail->empty[stage]), phase ^ 1);
@@ -449,7 +467,9 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
               }
             }
             // frees the smem slot (in both CTAs of a pair) when the MMAs retire
-            if (PAIR) umma_commit_pair(smem_u32(&tail->empty[stage]), 3); else umma_commit(smem_u32(&tail->empty[stage]));
+            if (PAIR) umma_commit_pair(smem_u32(&tail->empty[stage]), 3);
+            else if (CL > 1) umma_commit_multicast(smem_u32(&tail->empty[stage]), CL_MASK);
+            else umma_commit(smem_u32(&tail->empty[stage]));
             if (kb == kb1 - 1) {
               if (PAIR) umma_commit_pair(smem_u32(&tail->tmem_full[as]), 3); else umma_commit(smem_u32(&tail->tmem_full[as]));
 #ifdef FRX_TRACE
@@ -489,7 +509,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
       const int ks = item % P.k_splits, mi = item / P.k_splits;
       const int mu = mi % m_units, split = mi / m_units;
       if (unit_skipped(mu)) continue;
-      const int m_tile = PAIR ? 2 * mu + (int)crank : mu;     // this CTA's 128 accumulator lanes = these brand rows
+      const int m_tile = mu * UNIT + (int)crank;              // this CTA's 128 accumulator lanes = these brand rows
       const int64_t t0 = P.num_n_tiles * split / P.splits, t1 = P.num_n_tiles * (split + 1) / P.splits;
       const int row = m_tile * BM + row_in_tile;
       const bool row_ok = row < P.nb;
@@ -707,7 +727,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
   }
 #endif
   tc_fence_before();
-  if (PAIR) cluster_sync_all(); else __syncthreads();      // neither CTA of a pair exits while the other may still signal it
+  if (CLUSTERED) cluster_sync_all(); else __syncthreads();  // no CTA of a cluster exits while another may still signal it
   if (warp == 2) {
     tc_fence_after();
     if (PAIR) tmem_dealloc_pair<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -718,7 +738,15 @@ template <int MODE, bool TF32>
 __global__ void __maxnreg__(KERNEL_REGS)
 score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ ScoreParams P) {
-  score_body<MODE, TF32, false>(tmap_a, tmap_b, P);
+  score_body<MODE, TF32, false, 1>(tmap_a, tmap_b, P);
+}
+
+// The same kernel in clusters of CL CTAs that share every post tile through TMA multicast (cluster size given at launch).
+template <int MODE, bool TF32, int CL>
+__global__ void __maxnreg__(KERNEL_REGS)
+score_kernel_mc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const __grid_constant__ ScoreParams P) {
+  score_body<MODE, TF32, false, CL>(tmap_a, tmap_b, P);
 }
 
 // The same kernel on CTA pairs: clusters of two CTAs (the two SMs of a TPC), tcgen05 cta_group::2.
@@ -726,7 +754,7 @@ template <int MODE, bool TF32>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(KERNEL_REGS)
 score_kernel_pair(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ ScoreParams P) {
-  score_body<MODE, TF32, true>(tmap_a, tmap_b, P);
+  score_body<MODE, TF32, true, 1>(tmap_a, tmap_b, P);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1052,7 +1080,17 @@ static bool use_pair() {
   return v != 0 && num_sms() % 2 == 0;
 }
 
+// Third variant: clusters of CL CTAs sharing every post tile through TMA multicast (score_kernel_mc).  FRX_CLUSTER = 2 / 4 / 8
+// or frx_set_cluster(); bf16 operands only; 0 / 1 = off.
+static int g_cluster_mode = -1;
+static int use_cluster() {
+  static const int env = getenv("FRX_CLUSTER") ? atoi(getenv("FRX_CLUSTER")) : 0;
+  const int v = g_cluster_mode >= 0 ? g_cluster_mode : env;
+  return (v == 2 || v == 4 || v == 8) ? v : 1;
+}
+
 struct Plan {
+  int cluster;        // > 1: multicast clusters of this many CTAs (one scheduling unit = cluster x 128 brand rows)
   bool pair;          // one scheduling unit = a CTA pair working on 256 brand rows
   int num_m_tiles;    // 128-row m-tiles (padded to an even count for pairs: candidate lists are addressed by m-tile)
   int m_units, slots; // schedulable m-units (m-tiles or pairs of them) and concurrently resident units
@@ -1061,13 +1099,18 @@ struct Plan {
   size_t keys_bytes, cnt_bytes, thr_bytes;
 };
 
-static Plan make_plan(int nb, int64_t n_posts, int k, int mode) {
+static int max_active_clusters(int cl);
+
+static Plan make_plan(int nb, int64_t n_posts, int k, int mode, bool tf32 = false) {
   Plan p{};
-  p.pair = use_pair();
+  p.cluster = tf32 ? 1 : use_cluster();
+  p.pair = p.cluster == 1 && use_pair();
   const int real_m_tiles = (nb + BM - 1) / BM;
-  p.num_m_tiles = p.pair ? (real_m_tiles + 1) / 2 * 2 : real_m_tiles;
-  p.m_units = p.pair ? p.num_m_tiles / 2 : p.num_m_tiles;
-  p.slots = p.pair ? num_sms() / 2 : num_sms();
+  const int unit = p.pair ? 2 : p.cluster;
+  p.num_m_tiles = (real_m_tiles + unit - 1) / unit * unit;
+  p.m_units = p.num_m_tiles / unit;
+  p.slots = p.pair ? num_sms() / 2 : (p.cluster > 1 ? max_active_clusters(p.cluster) : num_sms());
+  if (p.slots < 1) { p.cluster = 1; p.pair = false; p.num_m_tiles = real_m_tiles; p.m_units = real_m_tiles; p.slots = num_sms(); }
   const int sms = p.slots;
   p.num_n_tiles = (n_posts + BN - 1) / BN;
   int64_t smax = p.num_n_tiles;
@@ -1084,7 +1127,7 @@ static Plan make_plan(int nb, int64_t n_posts, int k, int mode) {
   }
   p.splits = best;
   const long units = (long)p.m_units * p.splits;
-  p.grid = (int)(units < sms ? units : sms) * (p.pair ? 2 : 1);
+  p.grid = (int)(units < sms ? units : sms) * (p.pair ? 2 : p.cluster);
   const long items = (long)p.num_m_tiles * p.splits;             // candidate lists exist per (split, m-tile)
   int cap = 1024;
   while (cap < 4 * k) cap <<= 1;
@@ -1121,9 +1164,9 @@ struct TopkLayout {
   size_t total() const { return cnt_bytes + 2 * thr_bytes + hist_bytes + keys_bytes + dense_bytes + 256; }
 };
 
-static TopkLayout make_topk_layout(int nb, int64_t n_posts, int k) {
+static TopkLayout make_topk_layout(int nb, int64_t n_posts, int k, bool tf32 = false) {
   TopkLayout L{};
-  L.main = make_plan(nb, n_posts, k, MODE_TOPK);
+  L.main = make_plan(nb, n_posts, k, MODE_TOPK, tf32);
   L.cnt_bytes = L.main.cnt_bytes;
   L.keys_bytes = L.main.keys_bytes;
   L.thr_bytes = L.main.thr_bytes;
@@ -1142,15 +1185,63 @@ static TopkLayout make_topk_layout(int nb, int64_t n_posts, int k) {
     // small enough: dense sample tile + per-row k-th select (cheapest); else the fused top-k kernel on the sample
     L.sample_dense = (size_t)nb * (size_t)n_s * sizeof(float) <= ((size_t)1 << 30) && n_s <= 32768;
     if (L.sample_dense) {
-      L.sample = make_plan(nb, n_s, 1, MODE_DENSE);
+      L.sample = make_plan(nb, n_s, 1, MODE_DENSE, tf32);
       L.dense_bytes = (((size_t)nb * (size_t)n_s * sizeof(float)) + 255) & ~(size_t)255;
     } else {
-      L.sample = make_plan(nb, n_s, k, MODE_TOPK);
+      L.sample = make_plan(nb, n_s, k, MODE_TOPK, tf32);
       if (L.sample.cnt_bytes > L.cnt_bytes) L.cnt_bytes = L.sample.cnt_bytes;
       if (L.sample.keys_bytes > L.keys_bytes) L.keys_bytes = L.sample.keys_bytes;
     }
   }
   return L;
+}
+
+template <int MODE, int CL>
+static int launch_mc(int grid, const CUtensorMap& ma, const CUtensorMap& mb, const ScoreParams& P, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    FRX_CUDA(cudaFuncSetAttribute(score_kernel_mc<MODE, false, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = 1;
+  FRX_CUDA(cudaLaunchKernelEx(&cfg, score_kernel_mc<MODE, false, CL>, ma, mb, P));
+  return FRX_OK;
+}
+
+// resident clusters of `cl` multicast CTAs on this device (all modes have the same footprint)
+static int max_active_clusters(int cl) {
+  static int cached[9] = {0};
+  if (cl < 2 || cl > 8) return 0;
+  if (cached[cl]) return cached[cl] > 0 ? cached[cl] : 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(num_sms() / cl * cl));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = (unsigned)cl; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  cudaError_t e = cudaErrorInvalidValue;
+  if (cl == 2) { cudaFuncSetAttribute(score_kernel_mc<MODE_TOPK, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+                 e = cudaOccupancyMaxActiveClusters(&n, score_kernel_mc<MODE_TOPK, false, 2>, &cfg); }
+  if (cl == 4) { cudaFuncSetAttribute(score_kernel_mc<MODE_TOPK, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+                 e = cudaOccupancyMaxActiveClusters(&n, score_kernel_mc<MODE_TOPK, false, 4>, &cfg); }
+  if (cl == 8) { cudaFuncSetAttribute(score_kernel_mc<MODE_TOPK, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+                 e = cudaOccupancyMaxActiveClusters(&n, score_kernel_mc<MODE_TOPK, false, 8>, &cfg); }
+  if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+  cached[cl] = n > 0 ? n : -1;
+  return n;
 }
 
 template <int MODE, bool TF32>
@@ -1159,7 +1250,8 @@ static int launch_score(const void* a, int64_t ld_a, const void* b, int64_t ld_b
   CUtensorMap ma, mb;
   int rc = make_operand_map(&ma, a, nb, d, ld_a, BM, TF32);
   if (rc) return rc;
-  rc = make_operand_map(&mb, b, n_posts, d, ld_b, plan.pair ? BN / 2 : BN, TF32);   // a pair's CTAs load half a B tile each
+  // a pair's CTAs load half a B tile each; a multicast cluster's CTAs 1 / CL of it
+  rc = make_operand_map(&mb, b, n_posts, d, ld_b, plan.pair ? BN / 2 : BN / plan.cluster, TF32);
   if (rc) return rc;
   P.nb = nb;
   P.n_posts = n_posts;
@@ -1173,7 +1265,8 @@ static int launch_score(const void* a, int64_t ld_a, const void* b, int64_t ld_b
   P.trace = (MODE == MODE_TOPK && allow_probe) ? g_trace : nullptr;
   P.cta_trace = (MODE == MODE_TOPK && allow_probe) ? g_cta_trace : nullptr;
 #endif
-  if (plan.pair)
+  if (plan.cluster > 1 && !TF32) { /* attribute set in launch_mc */ }
+  else if (plan.pair)
     FRX_CUDA(cudaFuncSetAttribute(score_kernel_pair<MODE, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   else
     FRX_CUDA(cudaFuncSetAttribute(score_kernel<MODE, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -1188,8 +1281,12 @@ static int launch_score(const void* a, int64_t ld_a, const void* b, int64_t ld_b
     FRX_CUDA(cudaEventRecord(g_probe.beg[slot], st));
   }
   const long total_units = (long)plan.m_units * plan.splits * P.k_splits;
-  const int grid = (int)(total_units < plan.slots ? total_units : plan.slots) * (plan.pair ? 2 : 1);
-  if (plan.pair) score_kernel_pair<MODE, TF32><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);   // clusters of 2 CTAs
+  const int grid = (int)(total_units < plan.slots ? total_units : plan.slots) * (plan.pair ? 2 : plan.cluster);
+  if (plan.cluster > 1 && !TF32) {
+    rc = plan.cluster == 2 ? launch_mc<MODE, 2>(grid, ma, mb, P, st)
+       : plan.cluster == 4 ? launch_mc<MODE, 4>(grid, ma, mb, P, st) : launch_mc<MODE, 8>(grid, ma, mb, P, st);
+    if (rc) return rc;
+  } else if (plan.pair) score_kernel_pair<MODE, TF32><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);   // clusters of 2 CTAs
   else score_kernel<MODE, TF32><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
   FRX_LAUNCH_CHECK();
   if (probe) {
@@ -1232,7 +1329,7 @@ static int score_dense_impl(const void* a, int64_t ld_a, const void* b, int64_t 
   int rc = check_operands("frx_score_dense", a, ld_a, b, ld_b, nb, n_posts, d, 0, TF32);
   if (rc) return rc;
   FRX_CHECK_ARG(dense_out && ld_dense >= n_posts, "frx_score_dense: bad output");
-  Plan plan = make_plan(nb, n_posts, 1, MODE_DENSE);
+  Plan plan = make_plan(nb, n_posts, 1, MODE_DENSE, TF32);
   ScoreParams P{};
   P.ld_dense = ld_dense;
   // Small outputs (the B x B loss tile) cover only a few tiles: split K over the idle SMs and reduce afterwards.
@@ -1277,7 +1374,7 @@ static int score_count_impl(const void* a, int64_t ld_a, const void* b, int64_t 
   int rc = check_operands("frx_score_count", a, ld_a, b, ld_b, nb, n_posts, d, index_base, TF32);
   if (rc) return rc;
   FRX_CHECK_ARG(thr_score && thr_index && count_out, "frx_score_count: NULL pointer");
-  Plan plan = make_plan(nb, n_posts, 1, MODE_COUNT);
+  Plan plan = make_plan(nb, n_posts, 1, MODE_COUNT, TF32);
   ScoreParams P{};
   P.index_base = index_base;
   P.thr_score = thr_score;
@@ -1298,7 +1395,7 @@ static int score_topk_impl(const void* a, int64_t ld_a, const void* b, int64_t l
   FRX_CHECK_ARG((labels == nullptr) == (pos_score == nullptr), "frx_score_topk: labels and pos_score go together");
   FRX_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "frx_score_topk: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  const TopkLayout L = make_topk_layout(nb, n_posts, k);
+  const TopkLayout L = make_topk_layout(nb, n_posts, k, TF32);
   const Plan& plan = L.main;
   const size_t need = L.total();
   if (workspace == nullptr || workspace_bytes < need) {
@@ -1406,7 +1503,8 @@ extern "C" {
 size_t frx_score_topk_workspace_bytes(int nb, int64_t n_posts, int d, int k) {
   (void)d;
   if (nb <= 0 || n_posts <= 0 || k <= 0 || k > 1024) return 0;
-  return frx::make_topk_layout(nb, n_posts, k).total();
+  const size_t a = frx::make_topk_layout(nb, n_posts, k, false).total(), b = frx::make_topk_layout(nb, n_posts, k, true).total();
+  return a > b ? a : b;     // one query serves the bf16 and the tf32 entry points (their kernel variants may differ)
 }
 
 int frx_score_topk(const uint16_t* brand_bf16, int64_t ld_a, const uint16_t* post_bf16, int64_t ld_b, int nb,
@@ -1454,6 +1552,12 @@ int frx_debug_set_cta_trace(long long* device_buf) { frx::g_cta_trace = device_b
 int frx_set_cta_pairs(int on) {
   const int prev = frx::use_pair() ? 1 : 0;
   frx::g_pair_mode = on < 0 ? -1 : (on != 0 ? 1 : 0);
+  return prev;
+}
+
+int frx_set_cluster(int cta_count) {
+  const int prev = frx::use_cluster();
+  frx::g_cluster_mode = cta_count < 0 ? -1 : ((cta_count == 2 || cta_count == 4 || cta_count == 8) ? cta_count : 0);
   return prev;
 }
 

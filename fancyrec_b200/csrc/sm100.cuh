@@ -192,6 +192,25 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask
                : "memory");
 }
 
+// ---- cluster multicast (cta_group::1 MMAs, several CTAs share one B tile) ---------------------------------------
+// TMA load whose box lands at the SAME shared-memory offset in every CTA of `cta_mask` and completes bytes on the
+// mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int32_t c0,
+                                                      int32_t c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+// All previously issued MMAs of this CTA arrive, when they complete, on the barrier at this offset in EVERY CTA of
+// `cta_mask` (a shared-memory slot is free once every CTA that received the multicast tile has consumed it).
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask)
+               : "memory");
+}
+
 // ---- UMMA descriptors -----------------------------------------------------------------------
 // Shared-memory matrix descriptor for a K-major tile stored by TMA with SWIZZLE_128B:
 // rows of 128 bytes (64 bf16), 8-row swizzle atoms 1024 bytes apart.

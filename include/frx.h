@@ -332,6 +332,10 @@ int frx_probe_enable(int on);
  * -1 = back to the FRX_PAIR environment variable.  Results are identical bit for bit (same accumulation order per
  * output element).  Returns the previous setting.  Process-wide; not for concurrent use with running launches. */
 int frx_set_cta_pairs(int on);
+/* Third kernel variant of frx_score_*: clusters of `cta_count` (2, 4 or 8) CTAs on consecutive 128-brand tiles share every
+ * post tile through TMA multicast (each CTA fetches 1 / cta_count of it for all), bf16 operands.  0 or 1 = off (default), -1 =
+ * back to the FRX_CLUSTER environment variable.  Returns the previous setting.  Results are bit-identical in every variant. */
+int frx_set_cluster(int cta_count);
 int frx_probe_read(float* host_ms_out, int max);
 
 #ifdef __cplusplus
