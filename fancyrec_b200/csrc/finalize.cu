@@ -754,6 +754,24 @@ int frx_finalize_posts_bounded(const float* visual, const int64_t* row_ptr, cons
     int64_t blocks = n_posts;
     const int64_t max_blocks = (int64_t)num_sms() * (blocks_per_sm > 0 ? blocks_per_sm : (wide_unpooled || d > 3072 ? 4 : 5));
     if (blocks > max_blocks) blocks = max_blocks;
+    {
+      // A bounded launch is meant to run NEXT TO a resident contraction CTA, and a block can only join an SM whose
+      // shared-memory / L1 split matches its own: the contraction holds the maximum shared-memory carve-out, so ask for the
+      // same split (measured: without it the two kernels never co-reside -- the SM has to drain to change the split).  The
+      // default launch goes back to the default split (streaming loads are ~20 % faster with a normal L1).
+      static int carve_state = 0;                                 // 0 = default split, 1 = max shared
+      const int want = blocks_per_sm > 0 ? 1 : 0;
+      if (want != carve_state) {
+        const int v = want ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault;
+        cudaFuncSetAttribute(finalize_block_kernel<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+        cudaFuncSetAttribute(finalize_block_kernel<3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+        cudaFuncSetAttribute(finalize_block_kernel<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+        cudaFuncSetAttribute(finalize_block_kernel<3, true>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+        cudaFuncSetAttribute(finalize_block_kernel<4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+        cudaGetLastError();
+        carve_state = want;
+      }
+    }
     if (row_ptr != nullptr) {
       if (d <= 3072) finalize_block_kernel<3, true><<<(int)blocks, 256, 0, st>>>(P);
       else finalize_block_kernel<4, true><<<(int)blocks, 256, 0, st>>>(P);

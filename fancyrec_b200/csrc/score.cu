@@ -431,7 +431,8 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     setmaxnreg_dec<LEAN_REGS>();
-    if (lane == 0 && crank == 0) {                         // of a pair only the leader issues; its MMAs span both SMs
+    if (lane == 0 && (!PAIR || crank == 0)) {              // of a pair only the leader issues (its MMAs span both SMs);
+                                                           // in a multicast cluster every CTA issues its own
       constexpr int MMA_M = PAIR ? 2 * BM : BM;
       constexpr uint32_t idesc = TF32 ? make_idesc_tf32(MMA_M, BN) : make_idesc_bf16(MMA_M, BN);
       int stage = 0; uint32_t phase = 0;

@@ -456,3 +456,34 @@ def test_bad_arguments_raise():
         ops.score_topk(a, a, 2000)                       # k > 1024
     with pytest.raises(_lib.FrxError):
         ops.score_topk(a.cpu(), a, 4)                    # no CPU path
+
+
+@pytest.mark.parametrize("cl", [2, 4, 8])
+@pytest.mark.parametrize("nb,npost,d,k", [(300, 70001, 128, 100), (1000, 300000, 256, 64), (130, 5000, 96, 10), (5, 300, 64, 7)])
+def test_multicast_cluster_variant_bit_identical(cl, nb, npost, d, k):
+    """Clusters of 2 / 4 / 8 CTAs that share every post tile through TMA multicast (frx_set_cluster): fused top-k with the
+    score matrix written on the way, positives' scores and the count pass are bit for bit those of the single-CTA kernel
+    (m-tile counts that are not a multiple of the cluster size included: 300 brands = 3 m-tiles, 5 brands = 1)."""
+    from fancyrec_b200 import _lib, ops, ranking
+    lib = _lib.load()
+    g = torch.Generator(device=dev()).manual_seed(nb + npost + cl)
+    brand = ranking.to_operand(torch.randn((nb, d), generator=g, device=dev()))
+    post = ranking.to_operand(torch.randn((npost, d), generator=g, device=dev()))
+    labels = (torch.randperm(npost, generator=g, device=dev()) % nb).to(torch.int32)
+    prev = lib.frx_set_cluster(0)
+    try:
+        ref = ops.score_topk(brand, post, k, d=d, labels=labels, index_base=3)
+        refd = ops.score_dense(brand, post, d=d)
+        kk = min(k, npost) - 1
+        thr_s, thr_i = ref["scores"][:, kk // 2].contiguous(), ref["index"][:, kk // 2].contiguous()
+        refc = ops.score_count(brand, post, thr_s, thr_i, d=d, index_base=3)
+        lib.frx_set_cluster(cl)
+        got = ops.score_topk(brand, post, k, d=d, labels=labels, index_base=3, dense=True)
+        gotc = ops.score_count(brand, post, thr_s, thr_i, d=d, index_base=3)
+        gotd = ops.score_dense(brand, post, d=d)
+    finally:
+        lib.frx_set_cluster(prev if prev > 1 else 0)
+    assert torch.equal(got["index"], ref["index"]) and torch.equal(got["scores"], ref["scores"])
+    assert torch.equal(got["pos_score"], ref["pos_score"])
+    assert torch.equal(got["dense"], refd) and torch.equal(gotd, refd)
+    assert torch.equal(gotc, refc) and bool((refc == kk // 2).all())
