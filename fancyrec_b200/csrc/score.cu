@@ -48,15 +48,24 @@ struct Ring {
 constexpr int RING_BYTES = Ring<false>::STAGES * Ring<false>::STAGE_BYTES;   // 192 KB in both layouts
 static_assert(RING_BYTES == Ring<true>::STAGES * Ring<true>::STAGE_BYTES, "both ring layouts use the same shared memory");
 constexpr int EPI_WARP0 = 4;                 // warps 4..11: lane quarter = warp % 4, column half = (warp-4)/4
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = (EPI_WARP0 + NUM_EPI_WARPS) * 32;   // 384
+// Epilogue warps: 4 (one per TMEM lane quarter, each draining all 256 columns of a tile) or 8 (two per quarter, 128 columns
+// each).  The epilogue of a tile is 4-6 k of its 28 k cycles with 8 warps, so 4 warps still hide behind the next tile's MMAs,
+// and the CTA shrinks to 256 threads / 30 720 registers: room for TWO finalise blocks per SM next to it.
+#ifndef FRX_EPI_WARPS
+#define FRX_EPI_WARPS 4
+#endif
+constexpr int NUM_EPI_WARPS = FRX_EPI_WARPS;
+static_assert(NUM_EPI_WARPS == 4 || NUM_EPI_WARPS == 8, "one or two epilogue warps per TMEM lane quarter");
+constexpr int HALVES = NUM_EPI_WARPS / 4;                        // column ranges a tile is split into between the warps
+constexpr int NUM_THREADS = (EPI_WARP0 + NUM_EPI_WARPS) * 32;   // 256 or 384
 constexpr int TMEM_COLS = 512;
 // Register budget.  The CTA is launched with KERNEL_REGS per thread (52 224 of the SM's 65 536 registers), then the
 // warp group of the TMA / MMA / TMEM warps hands its surplus to the two epilogue warp groups (setmaxnreg):
 // 128 x 72 + 256 x 168 = 384 x 136.  What the CTA leaves free -- 13 312 registers and ~20 KB of shared memory -- is
 // exactly one 256-thread block of the post-finalisation kernel (<= 52 registers), so the HBM-bound finalisation of the
 // NEXT batch can run on the same SMs, from a second stream, while this batch is contracted (pipeline.py).
-constexpr int KERNEL_REGS = 136, LEAN_REGS = 72, EPI_REGS = 168;
+constexpr int LEAN_REGS = 72, EPI_REGS = 168;
+constexpr int KERNEL_REGS = (128 * LEAN_REGS + NUM_EPI_WARPS * 32 * EPI_REGS) / NUM_THREADS;     // 120 (4 warps) / 136 (8)
 static_assert(128 * LEAN_REGS + NUM_EPI_WARPS * 32 * EPI_REGS == NUM_THREADS * KERNEL_REGS, "register budget is redistributed exactly");
 constexpr int MAX_MERGE_KEYS = 16384;
 constexpr int MAX_NEED_TILES = 1024;          // COUNT mode tracks per-m-tile skip flags for up to 131072 brands
@@ -79,8 +88,8 @@ struct ScoreParams {
   int64_t index_base;
   // TOPK
   int k, cap, keep_limit;
-  unsigned long long* part_keys;   // [items][2 column halves][128][cap]
-  int* part_cnt;                   // [items][2][128]
+  unsigned long long* part_keys;   // [items][HALVES column ranges][128][cap]
+  int* part_cnt;                   // [items][HALVES][128]
   uint32_t* row_thr;               // [nb] best published lower bound of each row's k-th best score (ordered)
   uint32_t* row_hist;              // [nb][HIST_BINS] scores appended so far by ANY CTA, binned above row_base (nullptr = off)
   const uint32_t* row_base;        // [nb] ordered threshold seeded by the sample pass = origin of the bins (0 = row off)
@@ -493,7 +502,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
     const int h = (warp - EPI_WARP0) >> 2;
     const int ew = warp - EPI_WARP0;
     const int row_in_tile = q * 32 + lane;
-    constexpr int CHUNKS = BN / 2 / 32;              // 4 chunks of 32 columns per warp per tile
+    constexpr int CHUNKS = BN / HALVES / 32;         // chunks of 32 columns per warp per tile: 8 (4 warps) or 4 (8 warps)
     uint32_t* hist = tail->scratch[ew];
     float* stage = reinterpret_cast<float*>(tail->scratch[ew]);
     int as = 0; uint32_t aphase = 0;
@@ -523,7 +532,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
       float thr = row_ok ? -INFINITY : INFINITY;     // TOPK: append threshold
       int cnt = 0;                                   // TOPK: candidates buffered
       // candidate lists of this (split, m-tile, column half)
-      const size_t part = ((((size_t)split * P.num_m_tiles + m_tile) * P.k_splits + ks) * 2 + h) * BM;
+      const size_t part = ((((size_t)split * P.num_m_tiles + m_tile) * P.k_splits + ks) * HALVES + h) * BM;
       unsigned long long* rowbuf = nullptr;
       float ts = 0.f; int32_t ti = -1; unsigned long long ccount = 0;
       if (MODE == MODE_TOPK) rowbuf = P.part_keys + (part + row_in_tile) * P.cap;
@@ -536,7 +545,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
       if (MODE == MODE_COUNT && row_ok) { ts = P.thr_score[row]; ti = P.thr_index[row]; }
 
       for (int64_t t = t0; t < t1; ++t) {
-        const int64_t col0 = t * BN + h * (BN / 2);
+        const int64_t col0 = t * BN + h * (BN / HALVES);
         // issued before the accumulator wait so that their latency is hidden: the labels of this warp's
         // 128 columns and the row's global threshold (best lower bound published by any CTA so far)
         int lab[CHUNKS];
@@ -578,7 +587,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
 #pragma unroll 1
         for (int c = 0; c < CHUNKS; ++c) {
           uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + h * (BN / 2) + c * 32), v);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + h * (BN / HALVES) + c * 32), v);
           tmem_ld_wait();
           const int64_t cbase = col0 + c * 32;
           const int64_t rem = P.n_posts - cbase;
@@ -798,13 +807,13 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long
   __shared__ uint32_t hist[256];
   __shared__ int sel[3];
   const int b = blockIdx.x, m_tile = b / BM, r = b % BM;
-  const int lists = splits * 2;                 // (split, column half) -> list (split*num_m_tiles + m_tile)*2 + half
+  const int lists = splits * HALVES;            // (split, column range) -> list (split*num_m_tiles + m_tile)*HALVES + range
   auto list_ptr = [&](int s) {
-    return part_keys + ((((size_t)(s >> 1) * num_m_tiles + m_tile) * 2 + (s & 1)) * BM + r) * cap;
+    return part_keys + ((((size_t)(s / HALVES) * num_m_tiles + m_tile) * HALVES + (s % HALVES)) * BM + r) * cap;
   };
   // list sizes: loaded in parallel (one L2 round trip), then a serial prefix over shared memory
   for (int s = threadIdx.x; s < lists; s += blockDim.x)
-    offs[s + 1] = part_cnt[(((size_t)(s >> 1) * num_m_tiles + m_tile) * 2 + (s & 1)) * BM + r];
+    offs[s + 1] = part_cnt[(((size_t)(s / HALVES) * num_m_tiles + m_tile) * HALVES + (s % HALVES)) * BM + r];
   __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
@@ -1134,8 +1143,8 @@ static Plan make_plan(int nb, int64_t n_posts, int k, int mode, bool tf32 = fals
   while (cap < 4 * k) cap <<= 1;
   p.cap = cap;
   p.keep_limit = k + k / 4;
-  p.keys_bytes = (size_t)items * 2 * BM * cap * sizeof(unsigned long long);
-  p.cnt_bytes = (((size_t)items * 2 * BM * sizeof(int)) + 255) & ~(size_t)255;
+  p.keys_bytes = (size_t)items * HALVES * BM * cap * sizeof(unsigned long long);
+  p.cnt_bytes = (((size_t)items * HALVES * BM * sizeof(int)) + 255) & ~(size_t)255;
   p.thr_bytes = (((size_t)nb * sizeof(uint32_t)) + 255) & ~(size_t)255;
   return p;
 }
@@ -1421,7 +1430,7 @@ static int score_topk_impl(const void* a, int64_t ld_a, const void* b, int64_t l
   auto run_merge = [&](const Plan& pl) -> int {
     // shared memory: every candidate + the k survivors when that fits MAX_MERGE_KEYS, else just the sort buffer
     // (>= 2k keys) and the kernel streams the candidates from global memory
-    const size_t total_max = (size_t)pl.splits * 2 * (size_t)k;
+    const size_t total_max = (size_t)pl.splits * HALVES * (size_t)k;
     size_t np2 = 2;
     while (np2 < (size_t)2 * k) np2 <<= 1;
     size_t mkeys = total_max + k;

@@ -11,14 +11,16 @@ chunks of a post set larger than HBM -- this module keeps the device busy:
   * host          float64 aggregation (evaluator.py:129-143) of batch t-1 while the device works on batch t.
 
 `overlap=True` additionally moves the finalisation of batch t+1 to a side stream so that it runs UNDER the contraction of
-batch t (the contraction kernel is built to leave room on every SM for one finalise block, score.cu: KERNEL_REGS, and
-the side-stream launch is bounded to one block per SM).  Measured on B200 (tools/gpu_overlap_probe.py):
-the two kernels do co-reside, but the contraction relies on the CTAs that share a post tile running in lock step so that
-their L2 reads coalesce; a co-resident streaming kernel breaks that, operand traffic hits the L2 slice throughput cap and
-BOTH kernels run 2-2.6x slower (makespan 11 ms instead of 7.1 ms back to back).  It is therefore off by default.
+batch t: the contraction CTA (256 threads, 30 720 registers) leaves room on every SM for two finalise blocks, the
+side-stream launch is bounded to that many blocks and asks for the same shared-memory carve-out (a block only joins an SM
+whose shared-memory / L1 split matches its own).  Measured on B200 (tools/gpu_overlap_probe.py): the two
+kernels do overlap, and each runs 55-60 % slower while they do (they contend for L2 / HBM): 6.8 ms instead of 7.14 ms for the
+pair, 1 % on the pipelined step, and an isolated evaluation gets slower.  It is therefore off by default.
 
 Results are the same 8-tuples the synchronous call returns, bit for bit (tests/test_gpu_auc_pipeline.py).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -35,7 +37,8 @@ class EvalPipeline:
         self.group, self.want_auc, self.depth = group, want_auc, max(2, int(depth))
         self.visual_norm, self.text_norm = visual_norm, text_norm
         self.fin_stream = torch.cuda.Stream(self.dev) if overlap else None
-        self.side_blocks_per_sm = 1
+        self.main_stream = torch.cuda.Stream(self.dev)
+        self.side_blocks_per_sm = int(os.environ.get("FRX_SIDE_BLOCKS", "2"))   # finalise blocks per SM next to a contraction CTA
         ld = ops.round_up(self.d, 64)
         rows = 6 if want_auc else 5
         self.post_op = [torch.empty((n_posts_local, ld), dtype=torch.bfloat16, device=self.dev) for _ in range(self.depth)]
@@ -58,38 +61,47 @@ class EvalPipeline:
         slot = self.ticket % self.depth
         if self.pending[slot] is not None:
             self._collect(slot)
-        cur = torch.cuda.current_stream(self.dev)
+        caller = torch.cuda.current_stream(self.dev)
         post_op = self.post_op[slot]
-        fin = self.fin_stream
+        fin, main = self.fin_stream, self.main_stream
+        # The evaluation runs on the pipeline's OWN streams; they wait for what the caller has enqueued so far (the producer
+        # of the inputs), not for the evaluations submitted before this one.
+        inputs_ready = torch.cuda.Event()
+        inputs_ready.record(caller)
+        main.wait_event(inputs_ready)
+        for t in (w, e, visual, text, labels_i32):
+            if t is not None:
+                t.record_stream(main)
         if fin is not None:
-            inputs_ready = torch.cuda.Event()
-            inputs_ready.record(cur)
-            fin.wait_event(inputs_ready)                   # the caller produced visual / text on the current stream
+            fin.wait_event(inputs_ready)
             if self.op_free[slot] is not None:
                 fin.wait_event(self.op_free[slot])         # the contraction that last read this operand buffer is over
             with torch.cuda.stream(fin):
-                # one block per SM: what fits next to a resident contraction CTA (more would lock the contraction out)
+                # bounded launch: as many finalise blocks per SM as fit next to a resident contraction CTA
                 ops.finalize_posts(visual, text, visual_norm=self.visual_norm, text_norm=self.text_norm and text is not None,
                                    final_norm=True, out_bf16=post_op, blocks_per_sm=self.side_blocks_per_sm)
                 self.fin_done[slot].record(fin)
             for t in (visual, text):
                 if t is not None:
                     t.record_stream(fin)
-        else:
-            ops.finalize_posts(visual, text, visual_norm=self.visual_norm, text_norm=self.text_norm and text is not None,
-                               final_norm=True, out_bf16=post_op)
-        brand = ops.brand_embed(w, e, nb=self.nb)
-        brand_op = ops.finalize_posts(brand, final_norm=True)[1]
-        if fin is not None:
-            cur.wait_event(self.fin_done[slot])
-        st = sharded.sharded_rank_statistics(brand_op, post_op, labels_i32, self.d, self.k, self.n_total, group=self.group,
-                                             workspace=self.workspace, want_auc=self.want_auc)
-        self.workspace = st["workspace"]
-        packed = ranking.pack_statistics(st, self.want_auc)
-        self.host[slot].copy_(packed, non_blocking=True)
-        self.done[slot].record(cur)
-        free = torch.cuda.Event()
-        free.record(cur)
+        with torch.cuda.stream(main):
+            if fin is None:
+                if self.op_free[slot] is not None:
+                    main.wait_event(self.op_free[slot])
+                ops.finalize_posts(visual, text, visual_norm=self.visual_norm, text_norm=self.text_norm and text is not None,
+                                   final_norm=True, out_bf16=post_op)
+            brand = ops.brand_embed(w, e, nb=self.nb)
+            brand_op = ops.finalize_posts(brand, final_norm=True)[1]
+            if fin is not None:
+                main.wait_event(self.fin_done[slot])
+            st = sharded.sharded_rank_statistics(brand_op, post_op, labels_i32, self.d, self.k, self.n_total, group=self.group,
+                                                 workspace=self.workspace, want_auc=self.want_auc)
+            self.workspace = st["workspace"]
+            packed = ranking.pack_statistics(st, self.want_auc)
+            self.host[slot].copy_(packed, non_blocking=True)
+            self.done[slot].record(main)
+            free = torch.cuda.Event()
+            free.record(main)
         self.op_free[slot] = free
         self.last_stats, self.last_brand_op = st, brand_op
         ticket = self.ticket

@@ -45,7 +45,8 @@ for BPS in (0, 1, 2):
     a.record(); fin(post_b); b.record(); gemm(); c.record()
     torch.cuda.synchronize()
     print("alone (finalise blocks/SM bound %d): finalise" % BPS + " %.3f ms   score_topk call %.3f ms   sum %.3f" % (a.elapsed_time(b), b.elapsed_time(c), a.elapsed_time(c)))
-for order, BPS in (("gemm first", 0), ("finalise first", 0), ("gemm first", 1), ("finalise first", 1), ("gemm first", 2)):
+for order, BPS in (("gemm first", 0), ("finalise first", 0), ("gemm first", 1), ("finalise first", 1), ("gemm first", 2),
+                   ("finalise first", 2), ("finalise first", 3)):
     for rep in range(3):
         t0, g0, g1, f0, f1 = ev(), ev(), ev(), ev(), ev()
         torch.cuda.synchronize()
