@@ -48,24 +48,24 @@ struct Ring {
 constexpr int RING_BYTES = Ring<false>::STAGES * Ring<false>::STAGE_BYTES;   // 192 KB in both layouts
 static_assert(RING_BYTES == Ring<true>::STAGES * Ring<true>::STAGE_BYTES, "both ring layouts use the same shared memory");
 constexpr int EPI_WARP0 = 4;                 // warps 4..11: lane quarter = warp % 4, column half = (warp-4)/4
-// Epilogue warps: 4 (one per TMEM lane quarter, each draining all 256 columns of a tile) or 8 (two per quarter, 128 columns
-// each).  The epilogue of a tile is 4-6 k of its 28 k cycles with 8 warps, so 4 warps still hide behind the next tile's MMAs,
-// and the CTA shrinks to 256 threads / 30 720 registers: room for TWO finalise blocks per SM next to it.
-#ifndef FRX_EPI_WARPS
-#define FRX_EPI_WARPS 4
-#endif
-constexpr int NUM_EPI_WARPS = FRX_EPI_WARPS;
-static_assert(NUM_EPI_WARPS == 4 || NUM_EPI_WARPS == 8, "one or two epilogue warps per TMEM lane quarter");
-constexpr int HALVES = NUM_EPI_WARPS / 4;                        // column ranges a tile is split into between the warps
-constexpr int NUM_THREADS = (EPI_WARP0 + NUM_EPI_WARPS) * 32;   // 256 or 384
+// Epilogue warps: 4 (one per TMEM lane quarter, each draining all 256 columns of a tile; the default "slim" CTA of 256
+// threads / 30 720 registers) or 8 (two per quarter, 128 columns each; the "wide" CTA of 384 threads / 52 224 registers).
+// With 4 warps the epilogue of a tile is 8-11 k of its 28 k cycles at k <= 256 and still hides behind the next tile's MMAs
+// (config 2: step 8.0 ms against 8.15-8.35 ms with 8 warps, and two finalise blocks fit next to the CTA);
+// at k = 1000 the appends and compactions of the top-k epilogue need the 8 warps (config 4 on one GPU: 1.03 s against
+// 1.15 s), so the fused top-k launch picks the wide kernel for k > 256.
+constexpr int NUM_EPI_WARPS = 4, WIDE_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (EPI_WARP0 + NUM_EPI_WARPS) * 32;    // 256
+constexpr int WIDE_THREADS = (EPI_WARP0 + WIDE_EPI_WARPS) * 32;  // 384
+constexpr int WIDE_K = 256;                                       // fused top-k with k above this runs on the wide kernel
 constexpr int TMEM_COLS = 512;
-// Register budget.  The CTA is launched with KERNEL_REGS per thread (52 224 of the SM's 65 536 registers), then the
-// warp group of the TMA / MMA / TMEM warps hands its surplus to the two epilogue warp groups (setmaxnreg):
-// 128 x 72 + 256 x 168 = 384 x 136.  What the CTA leaves free -- 13 312 registers and ~20 KB of shared memory -- is
-// exactly one 256-thread block of the post-finalisation kernel (<= 52 registers), so the HBM-bound finalisation of the
-// NEXT batch can run on the same SMs, from a second stream, while this batch is contracted (pipeline.py).
+// Register budget.  A CTA is launched with a uniform count per thread, then the warp group of the TMA / MMA / TMEM
+// warps hands its surplus to the epilogue warp group(s) (setmaxnreg): 128 x 72 + 128 x 168 = 256 x 120 (slim),
+// 128 x 72 + 256 x 168 = 384 x 136 (wide).
 constexpr int LEAN_REGS = 72, EPI_REGS = 168;
-constexpr int KERNEL_REGS = (128 * LEAN_REGS + NUM_EPI_WARPS * 32 * EPI_REGS) / NUM_THREADS;     // 120 (4 warps) / 136 (8)
+constexpr int KERNEL_REGS = (128 * LEAN_REGS + NUM_EPI_WARPS * 32 * EPI_REGS) / NUM_THREADS;        // 120
+constexpr int WIDE_REGS = (128 * LEAN_REGS + WIDE_EPI_WARPS * 32 * EPI_REGS) / WIDE_THREADS;        // 136
+static_assert(128 * LEAN_REGS + WIDE_EPI_WARPS * 32 * EPI_REGS == WIDE_THREADS * WIDE_REGS, "register budget is redistributed exactly");
 static_assert(128 * LEAN_REGS + NUM_EPI_WARPS * 32 * EPI_REGS == NUM_THREADS * KERNEL_REGS, "register budget is redistributed exactly");
 constexpr int MAX_MERGE_KEYS = 16384;
 constexpr int MAX_NEED_TILES = 1024;          // COUNT mode tracks per-m-tile skip flags for up to 131072 brands
@@ -88,8 +88,8 @@ struct ScoreParams {
   int64_t index_base;
   // TOPK
   int k, cap, keep_limit;
-  unsigned long long* part_keys;   // [items][HALVES column ranges][128][cap]
-  int* part_cnt;                   // [items][HALVES][128]
+  unsigned long long* part_keys;   // [items][column ranges: 1 slim / 2 wide][128][cap]
+  int* part_cnt;                   // [items][column ranges][128]
   uint32_t* row_thr;               // [nb] best published lower bound of each row's k-th best score (ordered)
   uint32_t* row_hist;              // [nb][HIST_BINS] scores appended so far by ANY CTA, binned above row_base (nullptr = off)
   const uint32_t* row_base;        // [nb] ordered threshold seeded by the sample pass = origin of the bins (0 = row off)
@@ -114,7 +114,7 @@ struct SmemTail {
   uint32_t pad;
   // per epilogue warp: 256-bin radix histogram of the select (first 1 KB), or the 32 x 16 fp32 transpose stage of the
   // dense store (all 2 KB) -- never live at the same time
-  alignas(16) uint32_t scratch[NUM_EPI_WARPS][512];
+  alignas(16) uint32_t scratch[WIDE_EPI_WARPS][512];
   uint8_t tile_need[MAX_NEED_TILES];   // COUNT: m-tile has at least one row with a threshold (others are skipped)
 };
 constexpr size_t SMEM_BYTES = 1024 /* alignment slack */ + (size_t)RING_BYTES + sizeof(SmemTail);
@@ -322,9 +322,12 @@ __device__ __forceinline__ void store_dense_chunk_staged(float* base, int64_t ld
 // [c * 256 / CL, (c + 1) * 256 / CL) of it and TMA-multicasts them into the shared memory of all CL CTAs.  A ring slot is
 // free when ALL CTAs have consumed it (multicast MMA commits, `empty` counts CL arrivals).  Sharing the post operand no
 // longer depends on the CTAs of a range running in lock step so that their L2 reads coalesce.
-template <int MODE, bool TF32, bool PAIR, int CL>
+template <int MODE, bool TF32, bool PAIR, int CL, int EW>
 __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const ScoreParams& P) {
   static_assert(!(PAIR && CL > 1), "the CTA-pair variant and the multicast clusters are separate variants");
+  static_assert(EW == 4 || EW == 8, "one or two epilogue warps per TMEM lane quarter");
+  constexpr int HV = EW / 4;                               // column ranges a tile is split into between the epilogue warps
+  constexpr int NT = (EPI_WARP0 + EW) * 32;                // threads of this CTA
   constexpr bool CLUSTERED = PAIR || CL > 1;
   constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
   using R = Ring<PAIR>;
@@ -346,7 +349,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
       for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&tail->full[s]), 1); mbar_init(smem_u32(&tail->empty[s]), CL); }
       for (int s = 0; s < 2; ++s) {
         mbar_init(smem_u32(&tail->tmem_full[s]), 1);
-        mbar_init(smem_u32(&tail->tmem_empty[s]), NUM_EPI_WARPS * (PAIR ? 2 : 1));   // the leader hears both CTAs' epilogues
+        mbar_init(smem_u32(&tail->tmem_empty[s]), EW * (PAIR ? 2 : 1));   // the leader hears both CTAs' epilogues
       }
       fence_barrier_init();
     }
@@ -358,9 +361,9 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
       // rows without a threshold (thr_index < 0) are not counted; an m-tile made only of such rows is skipped by all
       // three roles, so the pass costs only the m-tiles that need it (nothing at all when no first positive is missing)
       const int nt = P.num_m_tiles < MAX_NEED_TILES ? P.num_m_tiles : MAX_NEED_TILES;
-      for (int i = threadIdx.x; i < nt; i += NUM_THREADS) tail->tile_need[i] = 0;
+      for (int i = threadIdx.x; i < nt; i += NT) tail->tile_need[i] = 0;
       __syncthreads();
-      for (int r = threadIdx.x; r < P.nb && r < MAX_NEED_TILES * BM; r += NUM_THREADS)
+      for (int r = threadIdx.x; r < P.nb && r < MAX_NEED_TILES * BM; r += NT)
         if (__ldg(P.thr_index + r) >= 0) tail->tile_need[r / BM] = 1;
     }
     tc_fence_before();
@@ -502,7 +505,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
     const int h = (warp - EPI_WARP0) >> 2;
     const int ew = warp - EPI_WARP0;
     const int row_in_tile = q * 32 + lane;
-    constexpr int CHUNKS = BN / HALVES / 32;         // chunks of 32 columns per warp per tile: 8 (4 warps) or 4 (8 warps)
+    constexpr int CHUNKS = BN / HV / 32;         // chunks of 32 columns per warp per tile: 8 (4 warps) or 4 (8 warps)
     uint32_t* hist = tail->scratch[ew];
     float* stage = reinterpret_cast<float*>(tail->scratch[ew]);
     int as = 0; uint32_t aphase = 0;
@@ -532,7 +535,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
       float thr = row_ok ? -INFINITY : INFINITY;     // TOPK: append threshold
       int cnt = 0;                                   // TOPK: candidates buffered
       // candidate lists of this (split, m-tile, column half)
-      const size_t part = ((((size_t)split * P.num_m_tiles + m_tile) * P.k_splits + ks) * HALVES + h) * BM;
+      const size_t part = ((((size_t)split * P.num_m_tiles + m_tile) * P.k_splits + ks) * HV + h) * BM;
       unsigned long long* rowbuf = nullptr;
       float ts = 0.f; int32_t ti = -1; unsigned long long ccount = 0;
       if (MODE == MODE_TOPK) rowbuf = P.part_keys + (part + row_in_tile) * P.cap;
@@ -545,7 +548,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
       if (MODE == MODE_COUNT && row_ok) { ts = P.thr_score[row]; ti = P.thr_index[row]; }
 
       for (int64_t t = t0; t < t1; ++t) {
-        const int64_t col0 = t * BN + h * (BN / HALVES);
+        const int64_t col0 = t * BN + h * (BN / HV);
         // issued before the accumulator wait so that their latency is hidden: the labels of this warp's
         // 128 columns and the row's global threshold (best lower bound published by any CTA so far)
         int lab[CHUNKS];
@@ -587,7 +590,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tmap_a, const CUte
 #pragma unroll 1
         for (int c = 0; c < CHUNKS; ++c) {
           uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + h * (BN / HALVES) + c * 32), v);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + h * (BN / HV) + c * 32), v);
           tmem_ld_wait();
           const int64_t cbase = col0 + c * 32;
           const int64_t rem = P.n_posts - cbase;
@@ -748,7 +751,15 @@ template <int MODE, bool TF32>
 __global__ void __maxnreg__(KERNEL_REGS)
 score_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ ScoreParams P) {
-  score_body<MODE, TF32, false, 1>(tmap_a, tmap_b, P);
+  score_body<MODE, TF32, false, 1, NUM_EPI_WARPS>(tmap_a, tmap_b, P);
+}
+
+// The wide CTA (8 epilogue warps, 384 threads): fused top-k at large k.
+template <int MODE, bool TF32>
+__global__ void __maxnreg__(WIDE_REGS)
+score_kernel_wide(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ ScoreParams P) {
+  score_body<MODE, TF32, false, 1, WIDE_EPI_WARPS>(tmap_a, tmap_b, P);
 }
 
 // The same kernel in clusters of CL CTAs that share every post tile through TMA multicast (cluster size given at launch).
@@ -756,7 +767,7 @@ template <int MODE, bool TF32, int CL>
 __global__ void __maxnreg__(KERNEL_REGS)
 score_kernel_mc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ ScoreParams P) {
-  score_body<MODE, TF32, false, CL>(tmap_a, tmap_b, P);
+  score_body<MODE, TF32, false, CL, NUM_EPI_WARPS>(tmap_a, tmap_b, P);
 }
 
 // The same kernel on CTA pairs: clusters of two CTAs (the two SMs of a TPC), tcgen05 cta_group::2.
@@ -764,7 +775,7 @@ template <int MODE, bool TF32>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(KERNEL_REGS)
 score_kernel_pair(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ ScoreParams P) {
-  score_body<MODE, TF32, true, 1>(tmap_a, tmap_b, P);
+  score_body<MODE, TF32, true, 1, NUM_EPI_WARPS>(tmap_a, tmap_b, P);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -799,7 +810,7 @@ __device__ __forceinline__ int next_pow2(int v) {
 __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long long* __restrict__ part_keys,
                                                              const int* __restrict__ part_cnt,
                                                              const uint32_t* __restrict__ row_thr, int num_m_tiles,
-                                                             int splits, int cap, int k, int smem_keys,
+                                                             int splits, int halves, int cap, int k, int smem_keys,
                                                              float* __restrict__ out_s, int32_t* __restrict__ out_i) {
   extern __shared__ unsigned long long skeys[];
   __shared__ int offs[2049];
@@ -807,13 +818,13 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const unsigned long
   __shared__ uint32_t hist[256];
   __shared__ int sel[3];
   const int b = blockIdx.x, m_tile = b / BM, r = b % BM;
-  const int lists = splits * HALVES;            // (split, column range) -> list (split*num_m_tiles + m_tile)*HALVES + range
+  const int lists = splits * halves;            // (split, column range) -> list (split*num_m_tiles + m_tile)*halves + range
   auto list_ptr = [&](int s) {
-    return part_keys + ((((size_t)(s / HALVES) * num_m_tiles + m_tile) * HALVES + (s % HALVES)) * BM + r) * cap;
+    return part_keys + ((((size_t)(s / halves) * num_m_tiles + m_tile) * halves + (s % halves)) * BM + r) * cap;
   };
   // list sizes: loaded in parallel (one L2 round trip), then a serial prefix over shared memory
   for (int s = threadIdx.x; s < lists; s += blockDim.x)
-    offs[s + 1] = part_cnt[(((size_t)(s / HALVES) * num_m_tiles + m_tile) * HALVES + (s % HALVES)) * BM + r];
+    offs[s + 1] = part_cnt[(((size_t)(s / halves) * num_m_tiles + m_tile) * halves + (s % halves)) * BM + r];
   __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
@@ -1101,6 +1112,8 @@ static int use_cluster() {
 
 struct Plan {
   int cluster;        // > 1: multicast clusters of this many CTAs (one scheduling unit = cluster x 128 brand rows)
+  bool wide;          // the 8-epilogue-warp CTA (fused top-k with k > WIDE_K on the default variant)
+  int halves;         // candidate lists per (item, brand row): 2 on the wide CTA, else 1
   bool pair;          // one scheduling unit = a CTA pair working on 256 brand rows
   int num_m_tiles;    // 128-row m-tiles (padded to an even count for pairs: candidate lists are addressed by m-tile)
   int m_units, slots; // schedulable m-units (m-tiles or pairs of them) and concurrently resident units
@@ -1143,8 +1156,10 @@ static Plan make_plan(int nb, int64_t n_posts, int k, int mode, bool tf32 = fals
   while (cap < 4 * k) cap <<= 1;
   p.cap = cap;
   p.keep_limit = k + k / 4;
-  p.keys_bytes = (size_t)items * HALVES * BM * cap * sizeof(unsigned long long);
-  p.cnt_bytes = (((size_t)items * HALVES * BM * sizeof(int)) + 255) & ~(size_t)255;
+  p.wide = mode == MODE_TOPK && !tf32 && p.cluster == 1 && !p.pair && k > WIDE_K;
+  p.halves = p.wide ? 2 : 1;
+  p.keys_bytes = (size_t)items * p.halves * BM * cap * sizeof(unsigned long long);
+  p.cnt_bytes = (((size_t)items * p.halves * BM * sizeof(int)) + 255) & ~(size_t)255;
   p.thr_bytes = (((size_t)nb * sizeof(uint32_t)) + 255) & ~(size_t)255;
   return p;
 }
@@ -1297,7 +1312,19 @@ static int launch_score(const void* a, int64_t ld_a, const void* b, int64_t ld_b
        : plan.cluster == 4 ? launch_mc<MODE, 4>(grid, ma, mb, P, st) : launch_mc<MODE, 8>(grid, ma, mb, P, st);
     if (rc) return rc;
   } else if (plan.pair) score_kernel_pair<MODE, TF32><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);   // clusters of 2 CTAs
-  else score_kernel<MODE, TF32><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
+  else if (plan.wide) {
+    if constexpr (MODE == MODE_TOPK && !TF32) {
+      static bool attr = false;
+      if (!attr) {
+        FRX_CUDA(cudaFuncSetAttribute(score_kernel_wide<MODE, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        attr = true;
+      }
+      score_kernel_wide<MODE, TF32><<<grid, WIDE_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
+    } else {
+      set_error("internal: the wide CTA exists for the bf16 fused top-k only");
+      return FRX_E_ARG;
+    }
+  } else score_kernel<MODE, TF32><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
   FRX_LAUNCH_CHECK();
   if (probe) {
     FRX_CUDA(cudaEventRecord(g_probe.end[slot], st));
@@ -1430,7 +1457,7 @@ static int score_topk_impl(const void* a, int64_t ld_a, const void* b, int64_t l
   auto run_merge = [&](const Plan& pl) -> int {
     // shared memory: every candidate + the k survivors when that fits MAX_MERGE_KEYS, else just the sort buffer
     // (>= 2k keys) and the kernel streams the candidates from global memory
-    const size_t total_max = (size_t)pl.splits * HALVES * (size_t)k;
+    const size_t total_max = (size_t)pl.splits * pl.halves * (size_t)k;
     size_t np2 = 2;
     while (np2 < (size_t)2 * k) np2 <<= 1;
     size_t mkeys = total_max + k;
@@ -1440,7 +1467,7 @@ static int score_topk_impl(const void* a, int64_t ld_a, const void* b, int64_t l
     const size_t msmem = mkeys * sizeof(unsigned long long);
     if (msmem > 32 * 1024)   // static smem (~10 KB) counts against the 48 KB default too
       FRX_CUDA(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-    merge_partials_kernel<<<nb, 256, msmem, st>>>(P.part_keys, P.part_cnt, P.row_thr, pl.num_m_tiles, pl.splits, pl.cap, k,
+    merge_partials_kernel<<<nb, 256, msmem, st>>>(P.part_keys, P.part_cnt, P.row_thr, pl.num_m_tiles, pl.splits, pl.halves, pl.cap, k,
                                                   (int)mkeys, topk_scores, topk_index);
     FRX_LAUNCH_CHECK();
     return FRX_OK;
