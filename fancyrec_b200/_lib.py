@@ -71,6 +71,7 @@ SIGNATURES = {
     "frx_brand_dropout_mask": (c_i32, [c_i32, c_i32, c_i32, ctypes.c_uint64, c_vp, c_vp]),
     "frx_linear_workspace_bytes": (c_sz, [c_i32, c_i32, c_i32]),
     "frx_linear": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "frx_matmul3x": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i64, c_vp, c_sz, c_vp]),
     "frx_metric_scores": (c_i32, [c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "frx_triplet_workspace_bytes": (c_sz, [c_i32, c_i32]),
     "frx_triplet_fwd_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

@@ -59,6 +59,7 @@ struct Gemm3xDesc {
 bool gemm3x_supported(const Gemm3xDesc& d);
 int gemm3x_plan_ksplit(const Gemm3xDesc* d, int count);                       // K split that fills the SMs (1 = none)
 size_t gemm3x_partial_floats(const Gemm3xDesc* d, int count, int ksplit);      // floats of the [ksplit][m][n] partial tiles
+size_t gemm3x_stream_floats(const Gemm3xDesc* d, int count);                   // floats of the stream mapping's shared-tile slots
 int gemm3x_launch(cudaStream_t st, const Gemm3xDesc* d, int count, int ksplit, bool keep_partials, float* partial,
                   size_t partial_floats);
 

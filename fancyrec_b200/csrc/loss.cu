@@ -409,7 +409,11 @@ static int gemm_nt(cudaStream_t st, bool tc, const TcScratch& ws, const float* x
 //   ks: K-split partial tiles of the B x B GEMMs (32 splits worth)
 static size_t xa_bytes(int b, int d, int nk) { return align256((size_t)b * 3 * (size_t)(d > nk ? d : nk) * sizeof(float)); }
 static size_t yb_bytes(int b, int d, int nk) { return align256((size_t)3 * d * (size_t)(b > nk ? b : nk) * sizeof(float)); }
-static size_t ks_bytes(int b) { return align256((size_t)b * b * sizeof(float) * 32); }
+// K-split partial tiles of the b x b products, or the shared-tile slots of the stream mapping (2 x 64 KB per SM)
+static size_t ks_bytes(int b) {
+  const size_t split = (size_t)b * b * sizeof(float) * 32, stream = (size_t)num_sms() * 2 * 128 * 128 * sizeof(float);
+  return align256(split > stream ? split : stream);
+}
 static size_t tc_scratch_bytes(int b, int d, int nk) { return xa_bytes(b, d, nk) + yb_bytes(b, d, nk) + ks_bytes(b); }
 
 // out = a + b (+ c), elementwise (gradient accumulation of separately computed GEMMs)
@@ -619,7 +623,7 @@ int frx_triplet_fwd_bwd(const int64_t* brand_ids, const float* brand, const floa
                       (void*)&rank_p, (void*)&rank_b, (void*)&diag, (void*)&ds_arg, (void*)&partial, (void*)&loss};
       FRX_CUDA(cudaLaunchCooperativeKernel((const void*)triplet_tile_kernel, dim3(b), dim3(256), args, tile_smem, st));
       if (d_post) {
-        rc = gemm3x_launch(st, gg, 2, 1, false, nullptr, 0);
+        rc = gemm3x_launch(st, gg, 2, 1, false, reinterpret_cast<float*>(ts.ksplit), avail);   // the tile stage has consumed the partial tiles
         if (rc) return rc;
       }
       return FRX_OK;

@@ -62,6 +62,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int32_t c0,
+                                            int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ---- TMEM / tcgen05 -------------------------------------------------------------------------
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {   // one full warp
@@ -224,6 +232,20 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
+  return d;
+}
+// MN-major tf32 operand tile: [MN / 32 groups][k rows][32 fp32 = 128 bytes] in the 128-byte swizzle with 32-byte atoms
+// (byte-address bits [5,7) ^= bits [7,9); TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; descriptor layout type 1) -- the
+// only MN-major layout the tensor core accepts for 32-bit elements.  The swizzle repeats every 4 k rows (512 bytes):
+// SBO = 512; LBO = byte distance between consecutive 128-byte MN groups (`group_bytes`).  One K = 8 instruction reads
+// two 4-row atoms of every group.
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t group_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(group_bytes >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
   return d;
 }
 // Instruction descriptor, kind::f16: D = fp32, A = B = bf16, both K-major, dense.

@@ -440,6 +440,33 @@ def linear(x, weight, bias=None, col_scale=None, relu=False, out=None):
     return out
 
 
+def matmul3x(a, b, a_transposed=False, b_transposed=False, alpha=1.0, out=None):
+    """out[M, N] = alpha * sum_k A(m, k) B(n, k) on the tensor cores, fp32-grade (the kernel behind `linear` and the
+    losses' gradient products).  A is a [M, K], or a [K, M] when a_transposed; B is b [N, K], or b [K, N] when
+    b_transposed -- transposed operands are read in place (no copy)."""
+    lib = _lib.load()
+    for name, t in (("a", a), ("b", b)) + ((("out", out),) if out is not None else ()):
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise _lib.FrxError("%s must be a CUDA tensor (fancyrec_b200 has no CPU fallback)" % name)
+        if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+            raise ValueError("%s must be a 2-D float32 tensor with unit column stride (row pitch is free)" % name)
+    k, m = (a.shape if a_transposed else a.shape[::-1])
+    kb, n = (b.shape if b_transposed else b.shape[::-1])
+    if k != kb:
+        raise ValueError("inner dimensions differ: %d vs %d" % (k, kb))
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    if m == 0 or n == 0:
+        return out
+    need = lib.frx_linear_workspace_bytes(m, n, k)
+    ws = torch.empty(need, dtype=torch.uint8, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = lib.frx_matmul3x(_ptr(a), a.stride(0), int(bool(a_transposed)), _ptr(b), b.stride(0), int(bool(b_transposed)),
+                              m, n, k, float(alpha), _ptr(out), out.stride(0), _ptr(ws), need, _stream(a))
+    _lib.check(rc, "frx_matmul3x")
+    return out
+
+
 SCORER_KINDS = {"P": 0, "AP": 1, "RR": 2, "NDCG": 3, "DCG": 4}
 _LOG2_TABLES = {}
 

@@ -249,6 +249,15 @@ size_t frx_linear_workspace_bytes(int m, int n, int k);
 int frx_linear(const float* x, int64_t ld_x, const float* w, int64_t ld_w, const float* col_scale, const float* col_shift,
                int relu, int m, int n, int k, float* out, int64_t ld_out, void* workspace, size_t workspace_bytes,
                void* stream);
+/* The same kernel as a plain product with either operand stored transposed -- the gradient products of the losses
+ * (loss.py:87-143: dPost = dS . brand, dBrand = dS^T . post) read dS and the embeddings in place:
+ *      out[m, n] = alpha * sum_k A(m, k) * B(n, k)
+ * A is a[m, ld_a] (a_transposed = 0) or a[k, ld_a] with A(m, k) = a[k * ld_a + m] (a_transposed = 1); B likewise with n
+ * rows.  Transposed operands whose row count is a multiple of 32 are fed to the tensor core as MN-major tiles (no
+ * transposition anywhere); others are transposed in shared memory.  Workspace: frx_linear_workspace_bytes(m, n, k). */
+int frx_matmul3x(const float* a, int64_t ld_a, int a_transposed, const float* b, int64_t ld_b, int b_transposed, int m,
+                 int n, int k, float alpha, float* out, int64_t ld_out, void* workspace, size_t workspace_bytes,
+                 void* stream);
 
 /* frx_metric_scores (A10; util/metric.py:6-123): the reference's rank-metric scorers over a BATCH of sorted label lists,
  * one warp per list.  labels int32 [n_lists, ld] (graded relevance, list i occupies labels[i*ld .. i*ld + lengths[i]);
