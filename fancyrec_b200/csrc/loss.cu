@@ -309,6 +309,65 @@ __global__ void __launch_bounds__(256) normalize_bwd_kernel(const float* __restr
     dx[(int64_t)r * d + c] = (dy[(int64_t)r * d + c] - y[(int64_t)r * d + c] * dot) / n;
 }
 
+// Both F.normalize calls of a loss in ONE launch (blocks [0, rows) -> x0, [rows, 2 rows) -> x1), 16-byte accesses when
+// the rows allow.
+__global__ void __launch_bounds__(256) normalize_rows2_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int rows,
+                                                               int d, float* __restrict__ y0, float* __restrict__ y1,
+                                                               float* __restrict__ n0, float* __restrict__ n1) {
+  __shared__ float red[8];
+  const bool second = (int)blockIdx.x >= rows;
+  const int r = second ? (int)blockIdx.x - rows : (int)blockIdx.x;
+  const float* x = (second ? x1 : x0) + (int64_t)r * d;
+  float* y = (second ? y1 : y0) + (int64_t)r * d;
+  const bool vec = d % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  float ss = 0.f;
+  if (vec) {
+    for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(x + c);
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  } else {
+    for (int c = threadIdx.x; c < d; c += blockDim.x) ss += x[c] * x[c];
+  }
+  ss = block_sum_float(ss, red);
+  const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+  if (vec) {
+    for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(x + c);
+      *reinterpret_cast<float4*>(y + c) = make_float4(v.x / nrm, v.y / nrm, v.z / nrm, v.w / nrm);
+    }
+  } else {
+    for (int c = threadIdx.x; c < d; c += blockDim.x) y[c] = x[c] / nrm;
+  }
+  float* no = second ? n1 : n0;
+  if (no && threadIdx.x == 0) no[r] = nrm;
+}
+
+// Both normalize backward passes of a loss in ONE launch; the second upstream gradient is the sum of up to three
+// separately computed products (dy1 = a + b + c, b / c optional), added on the fly.
+__global__ void __launch_bounds__(256) normalize_bwd2_kernel(const float* __restrict__ dy0, const float* __restrict__ y0,
+                                                              const float* __restrict__ nrm0, float* __restrict__ dx0,
+                                                              const float* __restrict__ dy1a, const float* __restrict__ dy1b,
+                                                              const float* __restrict__ dy1c, const float* __restrict__ y1,
+                                                              const float* __restrict__ nrm1, float* __restrict__ dx1,
+                                                              int rows, int d) {
+  __shared__ float red[8];
+  const bool second = (int)blockIdx.x >= rows;
+  const int r = second ? (int)blockIdx.x - rows : (int)blockIdx.x;
+  const int64_t o = (int64_t)r * d;
+  const float* a = (second ? dy1a : dy0) + o;
+  const float* b = second && dy1b ? dy1b + o : nullptr;
+  const float* c3 = second && dy1c ? dy1c + o : nullptr;
+  const float* y = (second ? y1 : y0) + o;
+  float* dx = (second ? dx1 : dx0) + o;
+  auto up = [&](int c) { return a[c] + (b ? b[c] : 0.f) + (c3 ? c3[c] : 0.f); };
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) dot += up(c) * y[c];
+  dot = block_sum_float(dot, red);
+  const float n = (second ? nrm1 : nrm0)[r];
+  for (int c = threadIdx.x; c < d; c += blockDim.x) dx[c] = (up(c) - y[c] * dot) / n;
+}
+
 // Row i of the cross-modal soft-max (loss_ctrs.py:166-177), in place:
 //   inter[i,:] (already / T)  -> d loss / d inter[i,:]
 //   ori[i,:]   (raw dots)     -> d loss / d ori[i,:]   (mask and 1/T folded in)
@@ -415,13 +474,6 @@ static size_t ks_bytes(int b) {
   return align256(split > stream ? split : stream);
 }
 static size_t tc_scratch_bytes(int b, int d, int nk) { return xa_bytes(b, d, nk) + yb_bytes(b, d, nk) + ks_bytes(b); }
-
-// out = a + b (+ c), elementwise (gradient accumulation of separately computed GEMMs)
-__global__ void add3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, int64_t n,
-                            float* __restrict__ out) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = a[i] + b[i] + (c ? c[i] : 0.f);
-}
 
 // ---------------------------------------------------------------------------------------------
 // A14: CrossCLR_onlyIntraModality (loss_ctrs.py:52-117) and LabLoss (loss.py:55-63) on the same tile machinery.
@@ -677,7 +729,7 @@ int frx_contrastive_fwd_bwd(const float* brand, const float* post, int b, int d,
   float* bn = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
   float* pn = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
   float* dbn = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
-  float* dpn = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
+  w += align256((size_t)b * d * 4);                              // (was: the summed d_pn; now formed inside normalize_bwd2)
   float* t1 = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
   float* t2 = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
   float* t3 = reinterpret_cast<float*>(w); w += align256((size_t)b * d * 4);
@@ -695,16 +747,22 @@ int frx_contrastive_fwd_bwd(const float* brand, const float* post, int b, int d,
   const bool tc = tc_ok(b, b, d) && b % 4 == 0 && nk % 4 == 0;
   const float inv_t = 1.0f / temperature;
   const float scale = mean_style ? 1.0f / (float)b : 1.0f;
-  // rank weight from the RAW tile (loss_ctrs.py:182-192)
-  int rc = gemm_nt(st, tc, ts, post, false, d, brand, false, d, inter, b, b, b, d, 1.f);
-  if (rc) return rc;
-  tile_rank_kernel<<<b, 128, 0, st>>>(inter, b, weight, rank_b, diag);
-  normalize_rows_kernel<<<b, 256, 0, st>>>(brand, d, bn, nrm_b);
-  normalize_rows_kernel<<<b, 256, 0, st>>>(post, d, pn, nrm_p);
+  normalize_rows2_kernel<<<2 * b, 256, 0, st>>>(brand, post, b, d, bn, pn, nrm_b, nrm_p);
   const float* kk = keys ? keys : pn;
-  // inter[i,j] = bn_i . pn_j / T ; ori[i,q] = pn_i . key_q
-  rc = gemm_nt(st, tc, ts, bn, false, d, pn, false, d, inter, b, b, b, d, inv_t);
+  // The RAW tile post . brand^T for the rank weights (loss_ctrs.py:182-192; parked in `ori`, which is written only after
+  // tile_rank has read it) and inter[i,j] = bn_i . pn_j / T: both B x B products in one grid.
+  float* raw_tile = ori;
+  const Gemm3xDesc gt[2] = {g3_desc(post, false, d, brand, false, d, raw_tile, b, b, b, d, 1.f),
+                            g3_desc(bn, false, d, pn, false, d, inter, b, b, b, d, inv_t)};
+  int rc = (tc && !g_loss_unfused) ? gemm3x_run(st, ts, gt, 2) : FRX_E_UNSUPPORTED;
+  if (rc == FRX_E_UNSUPPORTED) {
+    rc = gemm_nt(st, tc, ts, post, false, d, brand, false, d, raw_tile, b, b, b, d, 1.f);
+    if (rc) return rc;
+    rc = gemm_nt(st, tc, ts, bn, false, d, pn, false, d, inter, b, b, b, d, inv_t);
+  }
   if (rc) return rc;
+  tile_rank_kernel<<<b, 128, 0, st>>>(raw_tile, b, weight, rank_b, diag);
+  // ori[i,q] = pn_i . key_q
   rc = gemm_nt(st, tc, ts, pn, false, d, kk, false, d, ori, nk, b, nk, d, 1.f);
   if (rc) return rc;
   contrastive_row_kernel<<<b, 256, 0, st>>>(inter, ori, b, nk, mask_col0, no_intra, inv_t, negative_weight, scale,
@@ -733,14 +791,8 @@ int frx_contrastive_fwd_bwd(const float* brand, const float* post, int b, int d,
         sum3 = t3;
       }
     }
-    const float* dpn_src = t1;
-    if (sum2) {
-      const int64_t n = (int64_t)b * d;
-      add3_kernel<<<(int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>(t1, sum2, sum3, n, dpn);
-      dpn_src = dpn;
-    }
-    normalize_bwd_kernel<<<b, 256, 0, st>>>(dbn, bn, nrm_b, d, d_brand);
-    normalize_bwd_kernel<<<b, 256, 0, st>>>(dpn_src, pn, nrm_p, d, d_post);
+    // d_pn = t1 + t2 + t3 is formed inside the backward of the normalisation
+    normalize_bwd2_kernel<<<2 * b, 256, 0, st>>>(dbn, bn, nrm_b, d_brand, t1, sum2, sum3, pn, nrm_p, d_post, b, d);
   }
   FRX_LAUNCH_CHECK();
   return FRX_OK;
@@ -784,19 +836,30 @@ int frx_crossclr_fwd_bwd(const float* brand, const float* post, int b, int d, fl
   const float inv_t = 1.0f / temperature;
   const float scale = mean_style ? 0.5f / (float)b : 0.5f;
   float* pn = n1; float* bn = n1 + (size_t)b * d;
-  // rank weights from the RAW tile scores[i][j] = post_i . brand_j (loss_ctrs.py:62-77)
-  int rc = gemm_nt(st, tc, ts, post, false, d, brand, false, d, lbp, b, b, b, d, 1.f);
-  if (rc) return rc;
-  tile_rank_kernel<<<b, 128, 0, st>>>(lbp, b, rank_p, rank_b, diag);
-  normalize_rows_kernel<<<b, 256, 0, st>>>(post, d, pn, nrm_p);
-  normalize_rows_kernel<<<b, 256, 0, st>>>(brand, d, bn, nrm_b);
+  normalize_rows2_kernel<<<2 * b, 256, 0, st>>>(post, brand, b, d, pn, bn, nrm_p, nrm_b);
   FRX_CUDA(cudaMemcpyAsync(n2, bn, bd4, cudaMemcpyDeviceToDevice, st));
   FRX_CUDA(cudaMemcpyAsync(n2 + (size_t)b * d, pn, bd4, cudaMemcpyDeviceToDevice, st));
-  rc = gemm_nt(st, tc, ts, bn, false, d, pn, false, d, lbp, b, b, b, d, inv_t);
+  // Four B x B products, two per grid: the RAW tile scores[i][j] = post_i . brand_j for the rank weights
+  // (loss_ctrs.py:62-77; parked in g1, which crossclr_row_kernel overwrites later) with bn . pn^T / T, then the two Gram tiles.
+  float* raw_tile = g1;
+  const Gemm3xDesc ga[2] = {g3_desc(post, false, d, brand, false, d, raw_tile, b, b, b, d, 1.f),
+                            g3_desc(bn, false, d, pn, false, d, lbp, b, b, b, d, inv_t)};
+  const Gemm3xDesc gb[2] = {g3_desc(bn, false, d, bn, false, d, lbb, b, b, b, d, inv_t),
+                            g3_desc(pn, false, d, pn, false, d, lpp, b, b, b, d, inv_t)};
+  int rc = (tc && !g_loss_unfused) ? gemm3x_run(st, ts, ga, 2) : FRX_E_UNSUPPORTED;
+  if (rc == FRX_E_UNSUPPORTED) {
+    rc = gemm_nt(st, tc, ts, post, false, d, brand, false, d, raw_tile, b, b, b, d, 1.f);
+    if (rc) return rc;
+    rc = gemm_nt(st, tc, ts, bn, false, d, pn, false, d, lbp, b, b, b, d, inv_t);
+  }
   if (rc) return rc;
-  rc = gemm_nt(st, tc, ts, bn, false, d, bn, false, d, lbb, b, b, b, d, inv_t);
-  if (rc) return rc;
-  rc = gemm_nt(st, tc, ts, pn, false, d, pn, false, d, lpp, b, b, b, d, inv_t);
+  tile_rank_kernel<<<b, 128, 0, st>>>(raw_tile, b, rank_p, rank_b, diag);
+  rc = (tc && !g_loss_unfused) ? gemm3x_run(st, ts, gb, 2) : FRX_E_UNSUPPORTED;
+  if (rc == FRX_E_UNSUPPORTED) {
+    rc = gemm_nt(st, tc, ts, bn, false, d, bn, false, d, lbb, b, b, b, d, inv_t);
+    if (rc) return rc;
+    rc = gemm_nt(st, tc, ts, pn, false, d, pn, false, d, lpp, b, b, b, d, inv_t);
+  }
   if (rc) return rc;
   crossclr_row_kernel<<<b, 256, 0, st>>>(lbp, lbb, lpp, b, negative_weight, scale, rank_p, rank_b, g1, g2, partial);
   reduce_partials_kernel<<<1, 256, 0, st>>>(partial, b, scale, loss);
@@ -808,8 +871,7 @@ int frx_crossclr_fwd_bwd(const float* brand, const float* post, int b, int d, fl
     if (rc) return rc;
     rc = gemm_nt(st, tc2, ts, xp, false, 2 * b, n2, true, d, dpn, d, b, d, 2 * b, inv_t);   // d_pn = [G_bp^T | G_pp+G_pp^T] . [bn ; pn] / T
     if (rc) return rc;
-    normalize_bwd_kernel<<<b, 256, 0, st>>>(dbn, bn, nrm_b, d, d_brand);
-    normalize_bwd_kernel<<<b, 256, 0, st>>>(dpn, pn, nrm_p, d, d_post);
+    normalize_bwd2_kernel<<<2 * b, 256, 0, st>>>(dbn, bn, nrm_b, d_brand, dpn, nullptr, nullptr, pn, nrm_p, d_post, b, d);
   }
   FRX_LAUNCH_CHECK();
   return FRX_OK;
