@@ -1,3 +1,7 @@
+"""Device time of one MFC-sized Linear layer (512 x 3072 x 3072) on gemm3x, events around 20 launches, best of 5.
+Used for DESIGN.md 4.5's breakdown with a scratch build whose kernel honoured FRX_G3_DBG (bit 0: converters skip the split,
+bit 1: the issuer skips the MMAs -- results are then garbage, only the time means something); the shipped kernel has no such
+knob, FRX_G3_STREAM=0 (one CTA per tile instead of the stream mapping) is the only switch left."""
 import os, sys, torch
 sys.path.insert(0, "/root/repo")
 from fancyrec_b200 import ops
