@@ -75,6 +75,7 @@ SIGNATURES = {
     "frx_metric_scores": (c_i32, [c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "frx_triplet_workspace_bytes": (c_sz, [c_i32, c_i32]),
     "frx_triplet_fwd_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "frx_vsepp_fwd_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "frx_contrastive_workspace_bytes": (c_sz, [c_i32, c_i32, c_i32]),
     "frx_contrastive_fwd_bwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_f32, c_f32, c_i32,
                                         c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

@@ -614,6 +614,61 @@ __global__ void __launch_bounds__(256) l2norm_rows_kernel(const float* __restric
   if (norm_out && threadIdx.x == 0) norm_out[r] = nrm;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Opt-in: the hardest-negative ("max of violations", VSE++) hinge that north_star names and loss.py's ignored
+// `max_violation` flag stands for:  loss = sum_i max_j cost_p[i,j] + sum_j max_i cost_b[i,j]  with
+// cost_p = [m + S - S_ii]_+, cost_b = [m + S - S_jj]_+, same-brand entries zeroed as in loss.py:116-119, no rank weights.
+// Block i takes row i AND column i of the tile: the two maxima, their first positions (-1 when the maximum is 0: no
+// gradient), partial[i] = both maxima.
+__global__ void __launch_bounds__(256) vsepp_select_kernel(const float* __restrict__ s, const int64_t* __restrict__ ids, int b,
+                                                            float margin, int* __restrict__ row_arg, int* __restrict__ col_arg,
+                                                            float* __restrict__ partial) {
+  __shared__ float vmax[8];
+  __shared__ int vidx[8];
+  const int i = blockIdx.x;
+  const float dii = s[(int64_t)i * b + i];
+  const int64_t idi = ids[i];
+  float best[2] = {0.f, 0.f};
+  int arg[2] = {-1, -1};
+  for (int j = threadIdx.x; j < b; j += blockDim.x) {
+    if (ids[j] == idi) continue;
+    const float cp = margin + s[(int64_t)i * b + j] - dii;       // row i, negative brand j
+    const float cb = margin + s[(int64_t)j * b + i] - dii;       // column i, negative post j
+    if (cp > best[0]) { best[0] = cp; arg[0] = j; }
+    if (cb > best[1]) { best[1] = cb; arg[1] = j; }
+  }
+  float total = 0.f;
+  for (int w = 0; w < 2; ++w) {
+    float v = best[w]; int a = arg[w];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, a, o);
+      if (ov > v || (ov == v && oa >= 0 && (a < 0 || oa < a))) { v = ov; a = oa; }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { vmax[threadIdx.x >> 5] = v; vidx[threadIdx.x >> 5] = a; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < (int)(blockDim.x >> 5); ++k)
+        if (vmax[k] > v || (vmax[k] == v && vidx[k] >= 0 && (a < 0 || vidx[k] < a))) { v = vmax[k]; a = vidx[k]; }
+      (w == 0 ? row_arg : col_arg)[i] = v > 0.f ? a : -1;
+      total += v > 0.f ? v : 0.f;
+    }
+  }
+  if (threadIdx.x == 0) partial[i] = total;
+}
+// dS (zeroed before): +scale at the selected entries, -scale on the diagonal for each of them.  Sums of equal
+// magnitudes: exact in fp32, so the atomics' order does not matter.
+__global__ void __launch_bounds__(256) vsepp_scatter_kernel(const int* __restrict__ row_arg, const int* __restrict__ col_arg, int b,
+                                                             float scale, float* __restrict__ ds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  const int jr = row_arg[i], ic = col_arg[i];
+  if (jr >= 0) { atomicAdd(ds + (int64_t)i * b + jr, scale); atomicAdd(ds + (int64_t)i * b + i, -scale); }
+  if (ic >= 0) { atomicAdd(ds + (int64_t)ic * b + i, scale); atomicAdd(ds + (int64_t)i * b + i, -scale); }
+}
+
 }  // namespace frx
 
 extern "C" {
@@ -692,6 +747,53 @@ int frx_triplet_fwd_bwd(const int64_t* brand_ids, const float* brand, const floa
     rc = gemm_nt(st, tc, ts, ds, false, b, brand, true, d, d_post, d, b, d, b, 1.f);     // dPost  = dS   . brand
     if (rc) return rc;
     rc = gemm_nt(st, tc, ts, ds, true, b, post, true, d, d_brand, d, b, d, b, 1.f);      // dBrand = dS^T . post
+    if (rc) return rc;
+  }
+  FRX_LAUNCH_CHECK();
+  return FRX_OK;
+}
+
+int frx_vsepp_fwd_bwd(const int64_t* brand_ids, const float* brand, const float* post, int b, int d, float margin,
+                      int mean_style, float* loss, float* d_brand, float* d_post, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  using namespace frx;
+  FRX_CHECK_ARG(brand_ids && brand && post && loss, "frx_vsepp_fwd_bwd: NULL pointer");
+  FRX_CHECK_ARG(b > 0 && d > 0, "frx_vsepp_fwd_bwd: bad sizes");
+  FRX_CHECK_ARG((d_brand == nullptr) == (d_post == nullptr), "frx_vsepp_fwd_bwd: gradients go together");
+  if (!workspace || workspace_bytes < frx_triplet_workspace_bytes(b, d)) {
+    set_error("frx_vsepp_fwd_bwd: workspace %zu bytes, need %zu", workspace_bytes, frx_triplet_workspace_bytes(b, d));
+    return FRX_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+  float* s = reinterpret_cast<float*>(w); w += align256((size_t)b * b * 4);
+  float* ds = reinterpret_cast<float*>(w); w += align256((size_t)b * b * 4);
+  int* row_arg = reinterpret_cast<int*>(w); w += align256((size_t)b * 4);
+  int* col_arg = reinterpret_cast<int*>(w); w += align256((size_t)b * 4);
+  w += align256((size_t)b * 4);
+  float* partial = reinterpret_cast<float*>(w); w += align256((size_t)b * 4);
+  TcScratch ts;
+  ts.xa = reinterpret_cast<float*>(w); w += xa_bytes(b, d, b);
+  ts.yb = reinterpret_cast<float*>(w); w += yb_bytes(b, d, b);
+  ts.ksplit = w;
+  ts.ksplit_bytes = ks_bytes(b);
+  const bool tc = tc_ok(b, b, d) && b % 4 == 0;
+  const float scale = mean_style ? 1.0f / (float)b : 1.0f;
+  int rc = gemm_nt(st, tc, ts, post, false, d, brand, false, d, s, b, b, b, d, 1.f);      // S[i,j] = post_i . brand_j
+  if (rc) return rc;
+  vsepp_select_kernel<<<b, 256, 0, st>>>(s, brand_ids, b, margin, row_arg, col_arg, partial);
+  reduce_partials_kernel<<<1, 256, 0, st>>>(partial, b, scale, loss);
+  if (d_post) {
+    FRX_CUDA(cudaMemsetAsync(ds, 0, (size_t)b * b * sizeof(float), st));
+    vsepp_scatter_kernel<<<(b + 255) / 256, 256, 0, st>>>(row_arg, col_arg, b, scale, ds);
+    const Gemm3xDesc gg[2] = {g3_desc(ds, false, b, brand, true, d, d_post, d, b, d, b, 1.f),     // dPost  = dS   . brand
+                              g3_desc(ds, true, b, post, true, d, d_brand, d, b, d, b, 1.f)};     // dBrand = dS^T . post
+    rc = (tc && !g_loss_unfused) ? gemm3x_run(st, ts, gg, 2) : FRX_E_UNSUPPORTED;
+    if (rc == FRX_E_UNSUPPORTED) {
+      rc = gemm_nt(st, tc, ts, ds, false, b, brand, true, d, d_post, d, b, d, b, 1.f);
+      if (rc) return rc;
+      rc = gemm_nt(st, tc, ts, ds, true, b, post, true, d, d_brand, d, b, d, b, 1.f);
+    }
     if (rc) return rc;
   }
   FRX_LAUNCH_CHECK();

@@ -83,12 +83,32 @@ class _TripletFn(Function):
         return None, d_brand * grad_out, d_post * grad_out, None, None
 
 
+class _VseppFn(Function):
+    @staticmethod
+    def forward(ctx, brand_ids, brand_emb, post_emb, margin, mean_style):
+        want = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        loss, d_brand, d_post = ops.vsepp_fwd_bwd(brand_ids, brand_emb, post_emb, margin, mean_style, want)
+        if want:
+            ctx.save_for_backward(d_brand, d_post)
+        return loss.reshape(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        d_brand, d_post = ctx.saved_tensors
+        return None, d_brand * grad_out, d_post * grad_out, None, None
+
+
 class TripletLoss(nn.Module):
     """triplet ranking loss (rank-weighted hinge on the in-batch similarity tile)"""
 
     def __init__(self, margin=0, measure='cosine', max_violation=False, cost_style='sum', direction='all',
-                 loss_fun='mrl'):
+                 loss_fun='mrl', hardest_negative=False):
+        """The reference's constructor (loss.py:79-85): `max_violation`, `measure` and `loss_fun` are stored and never
+        read by forward -- so they are here.  `hardest_negative=True` is a NEW opt-in keyword (not in the reference): the
+        VSE++ hinge over the hardest in-batch negative of every row and column (frx_vsepp_fwd_bwd), no rank weights."""
         super(TripletLoss, self).__init__()
+        self.hardest_negative = bool(hardest_negative)
         self.margin = margin
         self.cost_style = cost_style
         self.direction = direction
@@ -102,5 +122,6 @@ class TripletLoss(nn.Module):
             raise TypeError("unsupported operand type(s) for *: 'Tensor' and 'NoneType' "
                             "(direction=%r; the reference only works with 'all')" % (self.direction,))
         ids = torch.as_tensor(brand_ids).to(brand_emb.device, torch.int64).contiguous()
-        return _TripletFn.apply(ids, brand_emb.contiguous().float(), post_emb.contiguous().float(),
-                                float(self.margin), 0 if self.cost_style == 'sum' else 1)
+        fn = _VseppFn if self.hardest_negative else _TripletFn
+        return fn.apply(ids, brand_emb.contiguous().float(), post_emb.contiguous().float(),
+                        float(self.margin), 0 if self.cost_style == 'sum' else 1)

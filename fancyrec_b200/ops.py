@@ -515,6 +515,25 @@ def triplet_fwd_bwd(brand_ids, brand, post, margin, mean_style, want_grad=True):
     return loss, d_brand, d_post
 
 
+def vsepp_fwd_bwd(brand_ids, brand, post, margin, mean_style, want_grad=True):
+    """Opt-in hardest-negative (VSE++) hinge on the in-batch tile: see frx_vsepp_fwd_bwd in include/frx.h."""
+    lib = _lib.load()
+    _req(brand_ids, torch.int64, "brand_ids", 1)
+    _req(brand, torch.float32, "brand", 2)
+    _req(post, torch.float32, "post", 2)
+    b, d = brand.shape
+    dev = brand.device
+    ws = torch.empty(lib.frx_triplet_workspace_bytes(b, d), dtype=torch.uint8, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    d_brand = torch.empty_like(brand) if want_grad else None
+    d_post = torch.empty_like(post) if want_grad else None
+    with torch.cuda.device(dev):
+        rc = lib.frx_vsepp_fwd_bwd(_ptr(brand_ids), _ptr(brand), _ptr(post), b, d, float(margin), int(mean_style),
+                                   _ptr(loss), _ptr(d_brand), _ptr(d_post), _ptr(ws), ws.numel(), _stream(brand))
+    _lib.check(rc, "frx_vsepp_fwd_bwd")
+    return loss, d_brand, d_post
+
+
 def normalize_rows(x):
     lib = _lib.load()
     _req(x, torch.float32, "x", 2)

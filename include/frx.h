@@ -295,6 +295,13 @@ size_t frx_triplet_workspace_bytes(int b, int d);
 int frx_triplet_fwd_bwd(const int64_t* brand_ids, const float* brand, const float* post, int b, int d,
                         float margin, int mean_style, float* loss, float* d_brand, float* d_post,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* Opt-in hardest-negative ("VSE++", max of violations) hinge on the same tile -- what loss.py's ignored `max_violation`
+ * flag stands for; NOT what TripletLoss.forward computes:
+ *   loss = sum_i max_j [m + S_ij - S_ii]_+  +  sum_j max_i [m + S_ij - S_jj]_+ , same-brand entries excluded
+ *   (loss.py:116-119), no rank weights; mean_style 1 divides by b.  Same outputs and workspace as frx_triplet_fwd_bwd. */
+int frx_vsepp_fwd_bwd(const int64_t* brand_ids, const float* brand, const float* post, int b, int d, float margin,
+                      int mean_style, float* loss, float* d_brand, float* d_post, void* workspace, size_t workspace_bytes,
+                      void* stream);
 
 /* A13  ContrastiveLoss (loss_ctrs.py:179-214), forward + backward.
  *   keys [n_keys, d]: the queue AFTER enqueue (loss_ctrs.py:138-147) or NULL for the

@@ -75,6 +75,37 @@ def triplet_loss(brand_ids, brand, post, margin=0.0, cost_style='sum', s_overrid
                                        pos_r=pos_r, pos_c=pos_c, active_p=~(mask | (xp < 0)), active_b=~(mask | (xb < 0)))
 
 
+def vsepp_loss(brand_ids, brand, post, margin=0.0, cost_style='sum', s_override=None):
+    """The hardest-negative hinge (VSE++, Faghri et al. 2018: `cost_s.max(1)[0] + cost_im.max(0)[0]`) on the reference's
+    tile S[i,j] = post_i . brand_j with its same-brand mask (loss.py:116-119) -- the mode loss.py's `max_violation` flag
+    names and never implements (checked against this restatement, never against loss.py).  No rank
+    weights; 'mean' divides by B.  Returns (loss, d_brand, d_post, aux); ties take the first position."""
+    brand = np.asarray(brand, np.float64)
+    post = np.asarray(post, np.float64)
+    ids = np.asarray(brand_ids)
+    b = brand.shape[0]
+    s = sim_tile(brand, post) if s_override is None else np.asarray(s_override, np.float64)
+    diag = np.diag(s)
+    mask = ids[:, None] == ids[None, :]
+    cost_p = np.where(mask, 0.0, np.maximum(margin + s - diag[:, None], 0.0))     # row i against S[i,i]
+    cost_b = np.where(mask, 0.0, np.maximum(margin + s - diag[None, :], 0.0))     # column j against S[j,j]
+    jr = cost_p.argmax(1)
+    ic = cost_b.argmax(0)
+    vr = cost_p[np.arange(b), jr]
+    vc = cost_b[ic, np.arange(b)]
+    scale = 1.0 if cost_style == 'sum' else 1.0 / b
+    loss = scale * (vr.sum() + vc.sum())
+    ds = np.zeros((b, b))
+    for i in range(b):
+        if vr[i] > 0:
+            ds[i, jr[i]] += scale
+            ds[i, i] -= scale
+        if vc[i] > 0:
+            ds[ic[i], i] += scale
+            ds[i, i] -= scale
+    return loss, ds.T @ post, ds @ brand, dict(s=s, ds=ds, row_arg=np.where(vr > 0, jr, -1), col_arg=np.where(vc > 0, ic, -1))
+
+
 def _normalize(x, eps=1e-12):
     n = np.maximum(np.sqrt((x * x).sum(1, keepdims=True)), eps)   # F.normalize
     return x / n, n

@@ -231,3 +231,44 @@ def test_lab_loss_vs_oracle_and_torch(b, d):
         torch.backends.cuda.matmul.allow_tf32 = prev
     want = br.grad.cpu().numpy()
     np.testing.assert_allclose(bt.grad.cpu().numpy(), want, rtol=2e-3, atol=2e-3 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("b,d,style", [(512, 3072, "sum"), (512, 1024, "mean"), (100, 96, "sum"), (33, 64, "mean")])
+def test_hardest_negative_hinge_opt_in(b, d, style):
+    """The opt-in VSE++ mode (`TripletLoss(hardest_negative=True)`, NOT the reference's forward): the selected negatives and
+    dS against the fp64 restatement evaluated on the device's own tile, the loss to 2e-5, and a 5-line torch autograd
+    restatement as a second witness."""
+    from fancyrec_b200 import loss as floss
+    from fancyrec_b200 import ops
+    rs = np.random.RandomState(7 * b + d)
+    ids = rs.randint(0, 23, b).astype(np.int64)
+    brand = (rs.standard_normal((b, d)) * 0.05).astype(np.float32)
+    post = (rs.standard_normal((b, d)) * 0.05).astype(np.float32) + brand * 0.5
+    crit = floss.TripletLoss(margin=0.2, cost_style=style, hardest_negative=True)
+    bt, pt = to_dev(brand).requires_grad_(), to_dev(post).requires_grad_()
+    val = crit(torch.from_numpy(ids), bt, pt)
+    val.backward()
+    # fp64 restatement on the tile the device used (aligned shapes: the same gemm3x product)
+    s_dev = ops.linear(to_dev(post), to_dev(brand)).cpu().numpy() if (d % 4 == 0 and b % 4 == 0 and b >= 32) else None
+    wl, wdb, wdp, aux = oloss.vsepp_loss(ids, brand, post, 0.2, style, s_override=s_dev)
+    np.testing.assert_allclose(val.item(), wl, rtol=2e-5)
+    if s_dev is not None:
+        np.testing.assert_allclose(bt.grad.cpu().numpy(), wdb, rtol=0, atol=1e-5 * np.abs(wdb).max())
+        np.testing.assert_allclose(pt.grad.cpu().numpy(), wdp, rtol=0, atol=1e-5 * np.abs(wdp).max())
+    # torch autograd witness (CPU, fp64)
+    tb = torch.from_numpy(brand).double().requires_grad_()
+    tp = torch.from_numpy(post).double().requires_grad_()
+    s = tp @ tb.t()
+    dg = s.diag()
+    same = torch.from_numpy(ids[:, None] == ids[None, :])
+    cost_p = (0.2 + s - dg[:, None]).clamp(min=0).masked_fill(same, 0)
+    cost_b = (0.2 + s - dg[None, :]).clamp(min=0).masked_fill(same, 0)
+    ref = cost_p.max(1)[0].sum() + cost_b.max(0)[0].sum()
+    if style == "mean":
+        ref = ref / b
+    ref.backward()
+    np.testing.assert_allclose(val.item(), ref.item(), rtol=1e-4)
+    np.testing.assert_allclose(bt.grad.cpu().numpy(), tb.grad.numpy(), rtol=0, atol=2e-3 * tb.grad.abs().max().item())
+    # the reference's own forward is untouched by the new keyword's default
+    plain = floss.TripletLoss(margin=0.2, cost_style=style, max_violation=True)
+    assert plain.hardest_negative is False

@@ -89,3 +89,31 @@ def test_crossclr_lab_golden(golden_dir):
         np.testing.assert_allclose(losses.crossclr_loss(brand, post, cost_style=style),
                                    g["crossclr_%s_loss" % style], rtol=2e-5)
     np.testing.assert_allclose(losses.lab_loss(brand), g["lab_loss"], rtol=1e-5)
+
+
+def test_vsepp_restatement_matches_torch_autograd():
+    """oracle.losses.vsepp_loss (the opt-in hardest-negative hinge; not a reference function) against torch autograd of
+    `cost_p.max(1) + cost_b.max(0)` on the reference's tile and same-brand mask, fp64."""
+    import torch
+    from oracle import losses as oloss
+    rs = np.random.RandomState(3)
+    b, d = 48, 24
+    ids = rs.randint(0, 9, b)
+    brand = rs.standard_normal((b, d)) * 0.3
+    post = rs.standard_normal((b, d)) * 0.3 + brand * 0.5
+    for style in ("sum", "mean"):
+        wl, wdb, wdp, _ = oloss.vsepp_loss(ids, brand, post, 0.2, style)
+        tb = torch.from_numpy(brand).requires_grad_()
+        tp = torch.from_numpy(post).requires_grad_()
+        s = tp @ tb.t()
+        dg = s.diag()
+        same = torch.from_numpy(ids[:, None] == ids[None, :])
+        cp = (0.2 + s - dg[:, None]).clamp(min=0).masked_fill(same, 0)
+        cb = (0.2 + s - dg[None, :]).clamp(min=0).masked_fill(same, 0)
+        ref = cp.max(1)[0].sum() + cb.max(0)[0].sum()
+        if style == "mean":
+            ref = ref / b
+        ref.backward()
+        np.testing.assert_allclose(wl, ref.item(), rtol=1e-12)
+        np.testing.assert_allclose(wdb, tb.grad.numpy(), atol=1e-12)
+        np.testing.assert_allclose(wdp, tp.grad.numpy(), atol=1e-12)
